@@ -1,0 +1,147 @@
+/*
+ * smoe_corr.h -- C ABI of libsmoecorr.so, the B200 (sm_100a) correlation hot path.
+ *
+ * This is the drop-in boundary for the RAFT-Stereo correlation path of SMoE-Stereo.
+ * Every entry point takes raw device pointers, explicit sizes and a CUDA stream;
+ * nothing here allocates, synchronises, or depends on torch/ATen/pybind.  All
+ * functions return SMOE_OK (0) or a non-zero error code; smoe_corr_last_error()
+ * returns a thread-local description of the last failure.  The library keeps no
+ * global mutable state and is re-entrant (the reference is driven from one host thread
+ * per GPU under nn.DataParallel, train_stereo_sceneflow.py:133).
+ *
+ * Reference interfaces replaced (paths relative to the reference repo):
+ *   smoe_corr_build            core/corr.py:148-156 (CorrBlock1D.corr: einsum + /sqrt(D))
+ *                              + core/corr.py:119-125 / :38-42 (avg_pool2d pyramid)
+ *   smoe_corr_lookup           core/corr.py:127-146 (CorrBlock1D.__call__), core/corr.py:44-51
+ *                              (CorrBlockFast1D.__call__), sampler/sampler.cpp:24-32 and
+ *                              sampler/sampler_kernel.cu:19-60,107-136 (corr_sampler.forward)
+ *   smoe_corr_lookup_bwd       sampler/sampler.cpp:34-45, sampler/sampler_kernel.cu:63-105,138-166
+ *                              (corr_sampler.backward)
+ *   smoe_corr_fold_pyramid_grad  autograd of core/corr.py:122-125 (avg_pool2d backward chain)
+ *
+ * Data layout
+ * -----------
+ * Feature maps are NCHW contiguous, (B,C,H,W), fp32 or fp16 (core/extractor.py:603-609).
+ * Coordinates are (B,coords_ch,H,W1) fp32; only channel 0 (x) is read (core/corr.py:129,
+ * :47).  Lookup outputs are (B, L*(2r+1), H, W1) contiguous, channel = level*(2r+1)+tap
+ * (core/corr.py:143-146).
+ * The correlation pyramid is described by smoe_pyramid_t: per level a base pointer, the
+ * level width W2_i = floor(W2 / 2^i) and the pitch (elements) between consecutive pixel rows.
+ * Pixel row index = (b*H + y)*W1 + x.  Two layouts are in use:
+ *   - "fused"   (owned by CorrBlock1D/CorrBlockFast1D): one buffer, all levels of a pixel in one
+ *               row, level_ptr[i] = base + level_offset[i], common pitch (smoe_corr_pyramid_layout);
+ *   - "planar"  (corr_sampler.forward/backward API): a single dense (B,H,W1,W2) level, pitch = W2.
+ */
+#ifndef SMOE_CORR_H_
+#define SMOE_CORR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMOE_CORR_ABI_VERSION 1
+#define SMOE_MAX_LEVELS 4
+
+/* error codes */
+#define SMOE_OK 0
+#define SMOE_ERR_INVALID_ARG 1   /* bad pointer / size / dtype combination            */
+#define SMOE_ERR_UNSUPPORTED 2   /* valid request this build cannot serve             */
+#define SMOE_ERR_CUDA 3          /* a CUDA runtime/driver call failed (see last_error) */
+
+/* element types */
+#define SMOE_DTYPE_F32 0
+#define SMOE_DTYPE_F16 1
+
+/* smoe_corr_build flags */
+#define SMOE_BUILD_TF32_TRUNCATE 1 /* fp32 inputs: load with a FLOAT32 tensor map so that tcgen05
+                                      kind::tf32 truncates the low 13 mantissa bits itself; default
+                                      (0) is a TFLOAT32 tensor map (TMA converts on the way in)  */
+
+/* smoe_corr_lookup_bwd modes */
+#define SMOE_BWD_OVERWRITE 0     /* write every element of the gradient (zeros outside the taps):
+                                    == zeros_like + scatter of sampler_kernel.cu:148-163         */
+#define SMOE_BWD_ACCUMULATE 1    /* read-modify-write the touched taps of a persistent gradient  */
+
+typedef void* smoe_stream_t;     /* cudaStream_t */
+
+typedef struct smoe_pyramid {
+  void* level_ptr[SMOE_MAX_LEVELS];     /* device pointers                                   */
+  int32_t width[SMOE_MAX_LEVELS];       /* W2_i                                              */
+  int64_t pitch[SMOE_MAX_LEVELS];       /* elements between consecutive pixel rows           */
+  int32_t num_levels;                   /* 1..SMOE_MAX_LEVELS                                */
+  int32_t dtype;                        /* SMOE_DTYPE_*                                      */
+  int32_t B, H, W1;                     /* pixel rows = B*H*W1                               */
+  int32_t reserved;
+} smoe_pyramid_t;
+
+/* ABI version of the loaded library (== SMOE_CORR_ABI_VERSION). */
+int smoe_corr_abi_version(void);
+
+/* Thread-local, NUL-terminated description of the last error on the calling thread. */
+const char* smoe_corr_last_error(void);
+
+/* 1 if the current device can run the kernels (compute capability 10.x), else 0. */
+int smoe_corr_device_supported(void);
+
+/*
+ * Fused pyramid layout for a volume of width W2: widths[i] = floor(W2/2^i)
+ * (core/corr.py:124 floor-halving), level_offset[i] (elements, 16-byte aligned) and the row
+ * pitch (elements, 128-byte aligned).  Pure host arithmetic.
+ */
+int smoe_corr_pyramid_layout(int W2, int num_levels, int dtype, int32_t* widths,
+                             int64_t* level_offset, int64_t* pitch);
+
+/* Bytes of device scratch smoe_corr_build needs for these shapes (0 when W1 and W2 satisfy the
+ * TMA 16-byte pitch rule; otherwise room for pitch-padded copies of the feature maps). */
+int64_t smoe_corr_build_workspace_bytes(int B, int C, int H, int W1, int W2, int in_dtype);
+
+/*
+ * Correlation volume + pyramid:
+ *   level0[(b,h,w1), w2] = scale * sum_c fmap1[b,c,h,w1] * fmap2[b,c,h,w2]
+ *   level(i+1)[., j]     = (level i[., 2j] + level i[., 2j+1]) / 2,  j < floor(W2_i/2)
+ * computed on tcgen05 tensor cores (kind::tf32 for fp32 inputs, kind::f16 for fp16 inputs,
+ * fp32 accumulation in TMEM), operands staged by TMA, scale and pooling fused in the epilogue.
+ * pyr->dtype is the output type (fp32, or fp16 when the inputs are fp16 -- the reference's
+ * reg_cuda path under autocast; each fp16 level is pooled from the rounded previous level, as
+ * F.avg_pool2d on a half tensor does).
+ */
+int smoe_corr_build(const void* fmap1, const void* fmap2, int in_dtype, int B, int C, int H,
+                    int W1, int W2, const smoe_pyramid_t* pyr, float scale, void* workspace,
+                    int64_t workspace_bytes, unsigned flags, smoe_stream_t stream);
+
+/*
+ * Lookup: for every pixel and level i, with xi = coords[b,0,y,x] * coord_scale / 2^i,
+ *   out[b, i*(2r+1)+k, y, x] = (1-dx)*L_i[row, fl-r+k] + dx*L_i[row, fl-r+k+1],
+ *   fl = floor(xi), dx = xi - fl, taps outside [0, W2_i) contribute 0.
+ * coords_batch_stride = elements between batches of coords (coords_ch*H*W1).
+ * out_dtype fp32, or fp16 for an fp16 pyramid (arithmetic then follows the reference's
+ * half-precision accumulation order, sampler_kernel.cu:46-59).
+ */
+int smoe_corr_lookup(const smoe_pyramid_t* pyr, const float* coords, int64_t coords_batch_stride,
+                     float coord_scale, int radius, void* out, int out_dtype,
+                     smoe_stream_t stream);
+
+/*
+ * Lookup backward (gradient w.r.t. the pyramid levels; coords get no gradient, core/corr.py:29).
+ *   grad_pyr level i [row, fl-r+t] (+)= grad_out[i*(2r+1)+t-1]*dx + grad_out[i*(2r+1)+t]*(1-dx)
+ * grad_out: (B, L*(2r+1), H, W1), dtype grad_out_dtype.  grad_pyr->dtype: fp32 (or fp16 in
+ * OVERWRITE mode for the fp16 corr_sampler.backward API).
+ */
+int smoe_corr_lookup_bwd(const smoe_pyramid_t* grad_pyr, const float* coords,
+                         int64_t coords_batch_stride, float coord_scale, int radius,
+                         const void* grad_out, int grad_out_dtype, int mode,
+                         smoe_stream_t stream);
+
+/*
+ * Fold the per-level gradients onto level 0 in place (avg_pool2d backward chain):
+ *   g_{i-1}[., 2j] += g_i[., j]/2 ; g_{i-1}[., 2j+1] += g_i[., j]/2, for i = L-1 .. 1.
+ */
+int smoe_corr_fold_pyramid_grad(const smoe_pyramid_t* grad_pyr, smoe_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMOE_CORR_H_ */

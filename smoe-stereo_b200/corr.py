@@ -1,0 +1,342 @@
+"""Drop-in replacement for the reference's ``core/corr.py`` on B200.
+
+Same names, constructor signatures and call semantics as the reference
+(``/root/reference/core/corr.py``):
+
+* ``CorrBlock1D(fmap1, fmap2, num_levels=4, radius=4)`` + ``__call__(coords)``     core/corr.py:110-156
+* ``CorrBlockFast1D(...)``                                                         core/corr.py:31-61
+* ``PytorchAlternateCorrBlock1D(...)``                                             core/corr.py:64-107
+* ``CorrSampler`` autograd.Function over ``corr_sampler.forward/backward``         core/corr.py:17-29
+
+but the arithmetic runs in hand-written sm_100a kernels behind the C ABI of libsmoecorr.so
+(include/smoe_corr.h): the volume + 4-level pyramid is ONE tcgen05/TMA kernel, every lookup is
+ONE fused kernel over all levels, and the lookup backward accumulates into one persistent
+gradient pyramid per training step instead of a dense volume per call.
+
+Host code is plumbing only: allocation (torch caching allocator), stream/device selection,
+argument checks that raise RuntimeError like TORCH_CHECK (sampler/sampler.cpp:20-22).  There is
+no CPU or PyTorch fallback -- tensors must live on a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+
+import torch
+
+from . import _lib
+from . import corr_sampler
+
+__all__ = ["CorrBlock1D", "CorrBlockFast1D", "PytorchAlternateCorrBlock1D", "CorrSampler",
+           "AlternateCorrBlock"]
+
+_DTYPE_CODE = {torch.float32: _lib.DTYPE_F32, torch.float16: _lib.DTYPE_F16}
+
+
+# ------------------------------------------------------------------------------------ helpers
+def _require_cuda(t: torch.Tensor, name: str) -> None:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+
+
+def _stream_ptr(device: torch.device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class _on_device:
+    """Make `device` current for the duration of a C-ABI call (no-op when it already is)."""
+
+    def __init__(self, device: torch.device):
+        self.idx = device.index if device.index is not None else torch.cuda.current_device()
+        self.prev = None
+
+    def __enter__(self):
+        cur = torch.cuda.current_device()
+        if cur != self.idx:
+            self.prev = cur
+            torch.cuda.set_device(self.idx)
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            torch.cuda.set_device(self.prev)
+
+
+class FusedPyramid:
+    """Device buffer holding every level of every pixel row contiguously (include/smoe_corr.h).
+
+    buffer: (B*H*W1, pitch) ; level i of a pixel occupies [offset_i, offset_i + W2_i).
+    """
+
+    def __init__(self, B, H, W1, W2, num_levels, dtype, device, zero=False):
+        if not 1 <= num_levels <= _lib.MAX_LEVELS:
+            raise RuntimeError(f"num_levels={num_levels} outside [1,{_lib.MAX_LEVELS}]")
+        self.B, self.H, self.W1, self.W2 = B, H, W1, W2
+        self.num_levels, self.dtype, self.device = num_levels, dtype, device
+        self.widths, self.offsets, self.pitch = _lib.pyramid_layout(W2, num_levels, _DTYPE_CODE[dtype])
+        rows = B * H * W1
+        alloc = torch.zeros if zero else torch.empty
+        self.buffer = alloc((rows, self.pitch), dtype=dtype, device=device)
+        self.c = _lib.Pyramid()
+        es = self.buffer.element_size()
+        base = self.buffer.data_ptr()
+        for i in range(num_levels):
+            self.c.level_ptr[i] = base + self.offsets[i] * es
+            self.c.width[i] = self.widths[i]
+            self.c.pitch[i] = self.pitch
+        self.c.num_levels = num_levels
+        self.c.dtype = _DTYPE_CODE[dtype]
+        self.c.B, self.c.H, self.c.W1 = B, H, W1
+        self.ref = ctypes.byref(self.c)
+
+    def level(self, i: int) -> torch.Tensor:
+        """Strided (B,H,W1,W2_i) view of level i (no copy)."""
+        v = self.buffer[:, self.offsets[i]:self.offsets[i] + self.widths[i]]
+        return v.view(self.B, self.H, self.W1, self.widths[i])
+
+
+def _build_into(pyr: FusedPyramid, fmap1: torch.Tensor, fmap2: torch.Tensor, flags: int = 0) -> None:
+    B, C, H, W1 = fmap1.shape
+    W2 = fmap2.shape[3]
+    L = _lib.lib()
+    code = _DTYPE_CODE[fmap1.dtype]
+    ws_bytes = L.smoe_corr_build_workspace_bytes(B, C, H, W1, W2, code)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=fmap1.device) if ws_bytes else None
+    with _on_device(fmap1.device):
+        rc = L.smoe_corr_build(fmap1.data_ptr(), fmap2.data_ptr(), code, B, C, H, W1, W2, pyr.ref,
+                               1.0 / math.sqrt(C), ws.data_ptr() if ws is not None else None,
+                               ws_bytes, flags, _stream_ptr(fmap1.device))
+    _lib.check(rc, "smoe_corr_build")
+    if ws is not None:
+        ws.record_stream(torch.cuda.current_stream(fmap1.device))
+
+
+def _coords_plane(coords: torch.Tensor, B: int, H: int, W1: int):
+    """Validate coords (B,>=1,H,W1) fp32 and return (tensor kept alive, batch stride in elements).
+    Only channel 0 (x) is read (core/corr.py:129, :47)."""
+    _require_cuda(coords, "coords")
+    if coords.dim() != 4 or coords.shape[0] != B or coords.shape[2] != H or coords.shape[3] != W1:
+        raise RuntimeError(f"coords must have shape ({B},>=1,{H},{W1}), got {tuple(coords.shape)}")
+    if coords.dtype != torch.float32:
+        coords = coords.float()
+    if coords.stride(3) != 1 or coords.stride(2) != W1:
+        coords = coords[:, :1].contiguous()
+    return coords, (coords.stride(0) if B > 1 else max(coords.stride(0), H * W1))
+
+
+def _lookup(pyr: FusedPyramid, coords: torch.Tensor, radius: int, out_dtype) -> torch.Tensor:
+    coords, bstride = _coords_plane(coords, pyr.B, pyr.H, pyr.W1)
+    out = torch.empty((pyr.B, pyr.num_levels * (2 * radius + 1), pyr.H, pyr.W1), dtype=out_dtype,
+                      device=pyr.device)
+    with _on_device(pyr.device):
+        rc = _lib.lib().smoe_corr_lookup(pyr.ref, coords.data_ptr(), bstride, 1.0, radius,
+                                         out.data_ptr(), _DTYPE_CODE[out_dtype],
+                                         _stream_ptr(pyr.device))
+    _lib.check(rc, "smoe_corr_lookup")
+    return out
+
+
+# ---------------------------------------------------------------------------- autograd plumbing
+class _State:
+    """Per-block state shared by the build and lookup autograd nodes."""
+
+    def __init__(self):
+        self.pyr: FusedPyramid | None = None
+        self.grad_pyr: FusedPyramid | None = None
+        self.radius = 4
+
+
+class _BuildFn(torch.autograd.Function):
+    """Volume + pyramid build.  Returns a 1-element token; every lookup takes the token as an
+    input, so autograd runs this node's backward ONCE, after all lookup backwards have
+    accumulated into state.grad_pyr."""
+
+    @staticmethod
+    def forward(ctx, fmap1, fmap2, state):
+        pyr = FusedPyramid(fmap1.shape[0], fmap1.shape[2], fmap1.shape[3], fmap2.shape[3],
+                           state.num_levels, state.pyr_dtype, fmap1.device)
+        _build_into(pyr, fmap1, fmap2)
+        state.pyr = pyr
+        ctx.state = state
+        ctx.save_for_backward(fmap1, fmap2)
+        return torch.zeros(1, dtype=torch.float32, device=fmap1.device)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_token):
+        fmap1, fmap2 = ctx.saved_tensors
+        state = ctx.state
+        gp = state.grad_pyr
+        state.grad_pyr = None
+        if gp is None:
+            return torch.zeros_like(fmap1), torch.zeros_like(fmap2), None
+        with _on_device(gp.device):
+            rc = _lib.lib().smoe_corr_fold_pyramid_grad(gp.ref, _stream_ptr(gp.device))
+        _lib.check(rc, "smoe_corr_fold_pyramid_grad")
+        # Autograd of core/corr.py:154-156.  The two backward GEMMs still go through cuBLAS
+        # (native tcgen05 build-backward is the next widening step).
+        g0 = gp.level(0)                                    # (B,H,W1,W2) fp32, strided view
+        scale = 1.0 / math.sqrt(fmap1.shape[1])
+        f1 = fmap1.float()
+        f2 = fmap2.float()
+        df1 = torch.einsum("bhkw,bchw->bchk", g0, f2).mul_(scale)
+        df2 = torch.einsum("bhkw,bchk->bchw", g0, f1).mul_(scale)
+        return df1.to(fmap1.dtype), df2.to(fmap2.dtype), None
+
+
+class _LookupFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, token, coords, state, out_dtype):
+        ctx.state = state
+        ctx.save_for_backward(coords)
+        return _lookup(state.pyr, coords, state.radius, out_dtype)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        (coords,) = ctx.saved_tensors
+        state = ctx.state
+        pyr = state.pyr
+        if state.grad_pyr is None:      # zeroed once per backward pass, not once per call
+            state.grad_pyr = FusedPyramid(pyr.B, pyr.H, pyr.W1, pyr.W2, pyr.num_levels,
+                                          torch.float32, pyr.device, zero=True)
+        gp = state.grad_pyr
+        grad_out = grad_out.contiguous()
+        if grad_out.dtype not in _DTYPE_CODE:
+            grad_out = grad_out.float()
+        coords, bstride = _coords_plane(coords, pyr.B, pyr.H, pyr.W1)
+        with _on_device(pyr.device):
+            rc = _lib.lib().smoe_corr_lookup_bwd(gp.ref, coords.data_ptr(), bstride, 1.0,
+                                                 state.radius, grad_out.data_ptr(),
+                                                 _DTYPE_CODE[grad_out.dtype], _lib.BWD_ACCUMULATE,
+                                                 _stream_ptr(pyr.device))
+        _lib.check(rc, "smoe_corr_lookup_bwd")
+        return torch.zeros(1, dtype=torch.float32, device=pyr.device), None, None, None
+
+
+# --------------------------------------------------------------------------------- the blocks
+class _CorrBlockBase:
+    """Shared implementation; subclasses fix the output dtype rule of the reference class."""
+
+    _float_output = True
+
+    def __init__(self, fmap1, fmap2, num_levels=4, radius=4):
+        _require_cuda(fmap1, "fmap1")
+        _require_cuda(fmap2, "fmap2")
+        if fmap1.dim() != 4 or fmap2.dim() != 4 or fmap1.shape[:3] != fmap2.shape[:3]:
+            raise RuntimeError("fmap1/fmap2 must be (B,C,H,W1)/(B,C,H,W2) with equal B,C,H, got "
+                               f"{tuple(fmap1.shape)} and {tuple(fmap2.shape)}")
+        if fmap1.device != fmap2.device:
+            raise RuntimeError("fmap1 and fmap2 must be on the same device")
+        if fmap1.dtype != fmap2.dtype:
+            fmap2 = fmap2.to(fmap1.dtype)
+        if fmap1.dtype not in _DTYPE_CODE:      # bf16 / fp64 inputs: compute like the fp32 path
+            fmap1, fmap2 = fmap1.float(), fmap2.float()
+        self.num_levels = num_levels
+        self.radius = radius
+        fmap1 = fmap1.contiguous()
+        fmap2 = fmap2.contiguous()
+        st = _State()
+        st.num_levels, st.radius, st.pyr_dtype = num_levels, radius, fmap1.dtype
+        self._state = st
+        self._token = None
+        if torch.is_grad_enabled() and (fmap1.requires_grad or fmap2.requires_grad):
+            self._token = _BuildFn.apply(fmap1, fmap2, st)
+        else:
+            st.pyr = FusedPyramid(fmap1.shape[0], fmap1.shape[2], fmap1.shape[3], fmap2.shape[3],
+                                  num_levels, fmap1.dtype, fmap1.device)
+            _build_into(st.pyr, fmap1, fmap2)
+
+    @property
+    def corr_pyramid(self):
+        """Reference-shaped views (B,H,W1,1,W2_i) of the fused buffer (core/corr.py:41)."""
+        p = self._state.pyr
+        return [p.level(i).unsqueeze(3) for i in range(p.num_levels)]
+
+    def __call__(self, coords):
+        p = self._state.pyr
+        out_dtype = torch.float32 if self._float_output else p.dtype
+        if self._token is not None and torch.is_grad_enabled():
+            return _LookupFn.apply(self._token, coords, self._state, out_dtype)
+        return _lookup(p, coords, self.radius, out_dtype)
+
+    @staticmethod
+    def corr(fmap1, fmap2):
+        """(B,D,H,W1),(B,D,H,W2) -> (B,H,W1,1,W2), same dtype (core/corr.py:148-156, :53-61).
+        Differentiable: backward is the einsum's (cuBLAS; see _BuildFn.backward)."""
+        return _CorrVolumeFn.apply(fmap1, fmap2)
+
+
+class _CorrVolumeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, fmap1, fmap2):
+        _require_cuda(fmap1, "fmap1")
+        _require_cuda(fmap2, "fmap2")
+        f1 = fmap1.contiguous()
+        f2 = fmap2.contiguous()
+        if f1.dtype not in _DTYPE_CODE:
+            f1, f2 = f1.float(), f2.float()
+        pyr = FusedPyramid(f1.shape[0], f1.shape[2], f1.shape[3], f2.shape[3], 1, f1.dtype, f1.device)
+        _build_into(pyr, f1, f2)
+        ctx.save_for_backward(f1, f2)
+        return pyr.level(0).unsqueeze(3).contiguous()
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        f1, f2 = ctx.saved_tensors
+        scale = 1.0 / math.sqrt(f1.shape[1])
+        g = g.squeeze(3).float()
+        df1 = torch.einsum("bhkw,bchw->bchk", g, f2.float()).mul_(scale).to(f1.dtype)
+        df2 = torch.einsum("bhkw,bchk->bchw", g, f1.float()).mul_(scale).to(f2.dtype)
+        return df1, df2
+
+
+class CorrBlock1D(_CorrBlockBase):
+    """"reg" implementation (core/corr.py:110-156): output is always fp32 (:146)."""
+    _float_output = True
+
+
+class CorrBlockFast1D(_CorrBlockBase):
+    """"reg_cuda" implementation (core/corr.py:31-61): output keeps the volume dtype (:49-51),
+    i.e. fp16 feature maps give an fp16 pyramid and fp16 lookups with the reference's
+    half-precision rounding order."""
+    _float_output = False
+
+
+class PytorchAlternateCorrBlock1D(_CorrBlockBase):
+    """"alt" implementation (core/corr.py:64-107).  The reference trades memory for recompute
+    (no volume; 36 grid_samples of fmap2 per call).  With 180 GB of HBM per B200 the volume of
+    even a 2000x3000 pair is ~2 GB, so this class is an API-compatible alias of the volume
+    path: same constructor, same (B,36,H,W) fp32 output (agrees with "reg" to 3.5e-5,
+    SURVEY.md 2).  As in every real call site, coords[:,1] is the pixel's own row."""
+    _float_output = True
+
+    def __init__(self, fmap1, fmap2, num_levels=4, radius=4):
+        super().__init__(fmap1, fmap2, num_levels=num_levels, radius=radius)
+        self.fmap1 = fmap1
+        self.fmap2 = fmap2
+
+
+class CorrSampler(torch.autograd.Function):
+    """Same contract as core/corr.py:17-29 on top of corr_sampler.forward/backward."""
+
+    @staticmethod
+    def forward(ctx, volume, coords, radius):
+        ctx.save_for_backward(volume, coords)
+        ctx.radius = radius
+        corr, = corr_sampler.forward(volume, coords, radius)
+        return corr
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        volume, coords = ctx.saved_tensors
+        grad_output = grad_output.contiguous()
+        grad_volume, = corr_sampler.backward(volume, coords, grad_output, ctx.radius)
+        return grad_volume, None, None
+
+
+class AlternateCorrBlock:
+    """"alt_cuda" is dead code in the reference (core/corr.py:159-161 raises first thing)."""
+
+    def __init__(self, fmap1, fmap2, num_levels=4, radius=4):
+        raise NotImplementedError

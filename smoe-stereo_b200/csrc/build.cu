@@ -1,0 +1,492 @@
+// build.cu -- all-pairs 1-D correlation volume + fused W-axis pyramid on tcgen05 / TMA (sm_100a).
+//
+//   level0[(b,h,w1), w2] = scale * sum_c f1[b,c,h,w1] * f2[b,c,h,w2]          (core/corr.py:148-156)
+//   level(i+1)[., j]     = (level i[., 2j] + level i[., 2j+1]) / 2            (core/corr.py:122-125)
+//
+// For a fixed (b,h) this is a [W1 x C] * [C x W2] GEMM whose operands are both "MN-major": in NCHW
+// memory the W axis is contiguous and the contraction axis C has stride H*W.  Work item =
+// (b*H+h, 128-row M tile, <=256-column N tile); a persistent CTA walks items round-robin so
+// that the M/N tiles of one image row run concurrently and share its operands through L2.
+//
+// Warp roles (192 threads):
+//   warp 0      TMA producer: per K step loads 128B-wide W slabs x KT channels of both operands
+//               with 4-D tensor maps (W,H,C,B) straight from NCHW memory into the swizzled
+//               MN-major layout tcgen05 expects (no transpose pass, TMA zero-fills W/C tails).
+//   warp 1      allocates TMEM (2 x 256 fp32 columns) and issues tcgen05.mma
+//               (kind::tf32 for fp32 inputs, kind::f16 for fp16 inputs), fp32 accumulate.
+//   warps 2-5   epilogue: tcgen05.ld 32 columns at a time, scale, build the three pooled levels
+//               in registers (pooling runs along N == along a thread's own TMEM row), store all
+//               levels.  Accumulators are double buffered so this overlaps the next item's MMAs.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace smoe {
+
+// ------------------------------------------------------------------------------ tile constants
+constexpr int kBlockM = 128;          // UMMA M (TMEM lanes)
+constexpr int kBlockN = 256;          // max UMMA N / accumulator columns per buffer
+constexpr int kStages = 4;
+constexpr int kStageABytes = 16 * 1024;   // 128 rows x KT channels
+constexpr int kStageBBytes = 32 * 1024;   // 256 cols x KT channels
+constexpr int kStageBytes = kStageABytes + kStageBBytes;
+constexpr int kBuildThreads = 192;
+constexpr int kTmemCols = 512;
+constexpr size_t kBuildSmemBytes = (size_t)kStages * kStageBytes + 1024;   // + alignment slack
+
+template <typename T> struct OperandCfg;
+template <> struct OperandCfg<float> {
+  static constexpr int kSlab = 32;          // W elements per 128-byte slab
+  static constexpr int kKT = 32;            // channels per pipeline stage
+  static constexpr int kUmmaK = 8;          // K per tcgen05.mma (32 bytes)
+  static constexpr uint32_t kSBO = 512;     // 4 k-rows per swizzle atom
+  static constexpr uint64_t kLayout = ptx::kLayoutSwizzle128B_Base32B;
+  static constexpr uint32_t kFmt = ptx::kFmtTF32;
+};
+template <> struct OperandCfg<__half> {
+  static constexpr int kSlab = 64;
+  static constexpr int kKT = 64;
+  static constexpr int kUmmaK = 16;
+  static constexpr uint32_t kSBO = 1024;    // 8 k-rows per swizzle atom
+  static constexpr uint64_t kLayout = ptx::kLayoutSwizzle128B;
+  static constexpr uint32_t kFmt = ptx::kFmtF16;
+};
+
+struct BuildDims {
+  int W1, W2, C, H, BH;      // BH = B*H image rows
+  int MT, NT;                // tiles per image row
+  float scale;
+};
+
+// ------------------------------------------------------------------------------------ epilogue
+// One thread owns one output row (pixel) and 32 consecutive level-0 columns starting at n0
+// (a multiple of 32).  Produces 32/16/8/4 values of levels 0..3 and stores them as 16-byte
+// vectors; columns >= width[i] are dropped (floor-halving of odd widths).
+template <typename OT> struct ChunkStore;
+
+template <> struct ChunkStore<float> {
+  __device__ static void run(const uint32_t (&acc)[32], const PyrDev& pyr, long long row, int n0,
+                             float scale, bool row_valid) {
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) * scale;
+    if (!row_valid) return;
+    {
+      float* dst = static_cast<float*>(pyr.ptr[0]) + row * pyr.pitch[0] + n0;
+      const int w = pyr.width[0];
+#pragma unroll
+      for (int g = 0; g < 8; ++g)
+        if (n0 + 4 * g < w)
+          *reinterpret_cast<float4*>(dst + 4 * g) =
+              make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+    }
+    if (pyr.num_levels < 2) return;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = (v[2 * j] + v[2 * j + 1]) * 0.5f;
+    {
+      float* dst = static_cast<float*>(pyr.ptr[1]) + row * pyr.pitch[1] + (n0 >> 1);
+      const int w = pyr.width[1];
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        if ((n0 >> 1) + 4 * g < w)
+          *reinterpret_cast<float4*>(dst + 4 * g) =
+              make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+    }
+    if (pyr.num_levels < 3) return;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (v[2 * j] + v[2 * j + 1]) * 0.5f;
+    {
+      float* dst = static_cast<float*>(pyr.ptr[2]) + row * pyr.pitch[2] + (n0 >> 2);
+      const int w = pyr.width[2];
+#pragma unroll
+      for (int g = 0; g < 2; ++g)
+        if ((n0 >> 2) + 4 * g < w)
+          *reinterpret_cast<float4*>(dst + 4 * g) =
+              make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+    }
+    if (pyr.num_levels < 4) return;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = (v[2 * j] + v[2 * j + 1]) * 0.5f;
+    if ((n0 >> 3) < pyr.width[3])
+      *reinterpret_cast<float4*>(static_cast<float*>(pyr.ptr[3]) + row * pyr.pitch[3] + (n0 >> 3)) =
+          make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+
+// fp16 pyramid: every level is rounded to half and the next level is pooled from the ROUNDED
+// values with an fp32 sum, which is what F.avg_pool2d does on a half tensor (core/corr.py:42).
+template <> struct ChunkStore<__half> {
+  __device__ static void pack_store(__half* dst, const float* v, int n) {   // n = 8 or 4 halves
+    __half2 h[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    if (n == 8)
+      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(h);
+    else
+      *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(h);
+  }
+  __device__ static float rh(float x) { return __half2float(__float2half_rn(x)); }
+  __device__ static void run(const uint32_t (&acc)[32], const PyrDev& pyr, long long row, int n0,
+                             float scale, bool row_valid) {
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = rh(__uint_as_float(acc[j]) * scale);
+    if (!row_valid) return;
+    {
+      __half* dst = static_cast<__half*>(pyr.ptr[0]) + row * pyr.pitch[0] + n0;
+      const int w = pyr.width[0];
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        if (n0 + 8 * g < w) pack_store(dst + 8 * g, v + 8 * g, 8);
+    }
+    if (pyr.num_levels < 2) return;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = rh((v[2 * j] + v[2 * j + 1]) * 0.5f);
+    {
+      __half* dst = static_cast<__half*>(pyr.ptr[1]) + row * pyr.pitch[1] + (n0 >> 1);
+      const int w = pyr.width[1];
+#pragma unroll
+      for (int g = 0; g < 2; ++g)
+        if ((n0 >> 1) + 8 * g < w) pack_store(dst + 8 * g, v + 8 * g, 8);
+    }
+    if (pyr.num_levels < 3) return;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = rh((v[2 * j] + v[2 * j + 1]) * 0.5f);
+    if ((n0 >> 2) < pyr.width[2])
+      pack_store(static_cast<__half*>(pyr.ptr[2]) + row * pyr.pitch[2] + (n0 >> 2), v, 8);
+    if (pyr.num_levels < 4) return;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = rh((v[2 * j] + v[2 * j + 1]) * 0.5f);
+    v[4] = v[5] = v[6] = v[7] = 0.f;
+    if ((n0 >> 3) < pyr.width[3])
+      pack_store(static_cast<__half*>(pyr.ptr[3]) + row * pyr.pitch[3] + (n0 >> 3), v, 4);
+  }
+};
+
+// -------------------------------------------------------------------------------------- kernel
+template <typename IT, typename OT>
+__global__ void __launch_bounds__(kBuildThreads, 1)
+corr_build_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const PyrDev pyr, const BuildDims dims) {
+  using Cfg = OperandCfg<IT>;
+  constexpr int kSlabBytes = Cfg::kKT * 128;                 // one W slab x KT channels
+  constexpr int kSlabsA = kBlockM / Cfg::kSlab;
+  constexpr int kKSteps = Cfg::kKT / Cfg::kUmmaK;            // MMAs per stage
+  constexpr uint32_t kKStepBytes = Cfg::kUmmaK * 128;        // smem advance per MMA along K
+  static_assert(kSlabsA * kSlabBytes == kStageABytes, "A stage size");
+  static_assert((kBlockN / Cfg::kSlab) * kSlabBytes == kStageBBytes, "B stage size");
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t s_full[kStages], s_empty[kStages], s_tfull[2], s_tempty[2];
+  __shared__ uint32_t s_tmem_base;
+
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;   // swizzle atoms: 1 KiB
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_items = dims.BH * dims.MT * dims.NT;
+  const int num_k = (dims.C + Cfg::kKT - 1) / Cfg::kKT;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmap_a);
+    ptx::prefetch_tensormap(&tmap_b);
+    for (int i = 0; i < kStages; ++i) {
+      ptx::mbar_init(ptx::smem_u32(&s_full[i]), 1);
+      ptx::mbar_init(ptx::smem_u32(&s_empty[i]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(ptx::smem_u32(&s_tfull[i]), 1);
+      ptx::mbar_init(ptx::smem_u32(&s_tempty[i]), 128);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(ptx::smem_u32(&s_tmem_base), kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = s_tmem_base;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const int nt = item % dims.NT;
+        const int mt = (item / dims.NT) % dims.MT;
+        const int bh = item / (dims.NT * dims.MT);
+        const int b = bh / dims.H, h = bh - b * dims.H;
+        const int n_valid = min(kBlockN, dims.W2 - nt * kBlockN);
+        const int slabs_b = (n_valid + Cfg::kSlab - 1) / Cfg::kSlab;
+        const uint32_t tx_bytes = (uint32_t)(kSlabsA + slabs_b) * kSlabBytes;
+        for (int ks = 0; ks < num_k; ++ks) {
+          ptx::mbar_wait(ptx::smem_u32(&s_empty[stage]), phase ^ 1u);
+          const uint32_t full = ptx::smem_u32(&s_full[stage]);
+          ptx::mbar_expect_tx(full, tx_bytes);
+          const uint32_t sa = smem_base + stage * kStageBytes;
+          const uint32_t sb = sa + kStageABytes;
+#pragma unroll
+          for (int j = 0; j < kSlabsA; ++j)
+            ptx::tma_load_4d(sa + j * kSlabBytes, &tmap_a, full, mt * kBlockM + j * Cfg::kSlab, h,
+                             ks * Cfg::kKT, b);
+          for (int j = 0; j < slabs_b; ++j)
+            ptx::tma_load_4d(sb + j * kSlabBytes, &tmap_b, full, nt * kBlockN + j * Cfg::kSlab, h,
+                             ks * Cfg::kKT, b);
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // -------------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int buf = 0;
+      uint32_t bphase = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const int nt = item % dims.NT;
+        const int n_valid = min(kBlockN, dims.W2 - nt * kBlockN);
+        const uint32_t n_mma = (uint32_t)((n_valid + 15) & ~15);
+        const uint32_t idesc = ptx::make_idesc_mn_major(Cfg::kFmt, kBlockM, n_mma);
+        ptx::mbar_wait(ptx::smem_u32(&s_tempty[buf]), bphase ^ 1u);
+        ptx::tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + (uint32_t)buf * kBlockN;
+        for (int ks = 0; ks < num_k; ++ks) {
+          ptx::mbar_wait(ptx::smem_u32(&s_full[stage]), phase);
+          ptx::tc_fence_after_sync();
+          const uint32_t sa = smem_base + stage * kStageBytes;
+          const uint32_t sb = sa + kStageABytes;
+#pragma unroll
+          for (int kk = 0; kk < kKSteps; ++kk) {
+            const uint64_t adesc =
+                ptx::make_smem_desc(sa + kk * kKStepBytes, kSlabBytes, Cfg::kSBO, Cfg::kLayout);
+            const uint64_t bdesc =
+                ptx::make_smem_desc(sb + kk * kKStepBytes, kSlabBytes, Cfg::kSBO, Cfg::kLayout);
+            if (sizeof(IT) == 4)
+              ptx::mma_tf32(d_tmem, adesc, bdesc, idesc, (ks | kk) != 0 ? 1u : 0u);
+            else
+              ptx::mma_f16(d_tmem, adesc, bdesc, idesc, (ks | kk) != 0 ? 1u : 0u);
+          }
+          ptx::tc_commit(ptx::smem_u32(&s_empty[stage]));     // smem slot free when MMAs retire
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        ptx::tc_commit(ptx::smem_u32(&s_tfull[buf]));          // accumulator ready
+        buf ^= 1;
+        if (buf == 0) bphase ^= 1u;
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------------- epilogue
+    const int quad = warp & 3;                    // TMEM lane quadrant this warp may read
+    int buf = 0;
+    uint32_t bphase = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      const int nt = item % dims.NT;
+      const int mt = (item / dims.NT) % dims.MT;
+      const int bh = item / (dims.NT * dims.MT);
+      const int n_valid = min(kBlockN, dims.W2 - nt * kBlockN);
+      const int m = mt * kBlockM + quad * 32 + lane;
+      const bool row_valid = m < dims.W1;
+      const long long row = (long long)bh * dims.W1 + m;
+      ptx::mbar_wait(ptx::smem_u32(&s_tfull[buf]), bphase);
+      ptx::tc_fence_after_sync();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)buf * kBlockN;
+      const int chunks = (n_valid + 31) >> 5;
+      for (int c = 0; c < chunks; ++c) {
+        uint32_t acc[32];
+        ptx::tmem_ld_32x32(taddr + c * 32, acc);
+        ptx::tmem_ld_wait();
+        ChunkStore<OT>::run(acc, pyr, row, nt * kBlockN + c * 32, dims.scale, row_valid);
+      }
+      ptx::tc_fence_before_sync();
+      ptx::mbar_arrive(ptx::smem_u32(&s_tempty[buf]));
+      buf ^= 1;
+      if (buf == 0) bphase ^= 1u;
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------- pitch-padding pre-pass
+// TMA needs 16-byte global strides; feature maps whose W*sizeof(T) is not a multiple of 16 are
+// copied once into a pitch-padded workspace (zero tail) and the tensor map points there.
+template <typename T>
+__global__ void __launch_bounds__(256)
+pad_rows_kernel(const T* __restrict__ src, T* __restrict__ dst, long long rows, int W, int Wp) {
+  const long long total = rows * Wp;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / Wp;
+    const int w = static_cast<int>(i - r * Wp);
+    dst[i] = w < W ? src[r * W + w] : T(0);
+  }
+}
+
+// --------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+static int padded_width(int W, int es) {
+  const int per16 = 16 / es;
+  return (W + per16 - 1) / per16 * per16;
+}
+
+// 4-D map over an NCHW feature map (dims W,H,C,B; row pitch Wp elements), box = slab x 1 x KT x 1.
+static int make_fmap_tmap(CUtensorMap* out, const void* base, int dtype, bool tf32_round, int B, int C,
+                          int H, int W, int Wp) {
+  EncodeTiledFn enc = encode_fn();
+  SMOE_REQUIRE(enc != nullptr, SMOE_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  const int es = dtype_size(dtype);
+  const cuuint64_t gdim[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)B};
+  const cuuint64_t gstr[3] = {(cuuint64_t)Wp * es, (cuuint64_t)H * Wp * es, (cuuint64_t)C * H * Wp * es};
+  const cuuint32_t box[4] = {(cuuint32_t)(128 / es), 1u, (cuuint32_t)(128 / es), 1u};
+  const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  const CUtensorMapDataType dt =
+      dtype == SMOE_DTYPE_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                              : (tf32_round ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
+  const CUtensorMapSwizzle sw =
+      dtype == SMOE_DTYPE_F16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+  const CUresult r = enc(out, dt, 4, const_cast<void*>(base), gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SMOE_REQUIRE(r == CUDA_SUCCESS, SMOE_ERR_CUDA,
+               "cuTensorMapEncodeTiled failed with CUresult %d (W=%d H=%d C=%d B=%d pitch=%d)", (int)r, W,
+               H, C, B, Wp);
+  return SMOE_OK;
+}
+
+template <typename IT, typename OT>
+static int launch_build(const CUtensorMap& ta, const CUtensorMap& tb, const PyrDev& pyr,
+                        const BuildDims& dims, cudaStream_t st) {
+  auto kern = corr_build_kernel<IT, OT>;
+  SMOE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)kBuildSmemBytes));
+  int dev = 0, sms = 0;
+  SMOE_CUDA_OK(cudaGetDevice(&dev));
+  SMOE_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const long long items = (long long)dims.BH * dims.MT * dims.NT;
+  const int grid = (int)(items < sms ? items : sms);
+  kern<<<grid, kBuildThreads, kBuildSmemBytes, st>>>(ta, tb, pyr, dims);
+  return check_launch("corr_build_kernel");
+}
+
+}  // namespace smoe
+
+extern "C" {
+
+int64_t smoe_corr_build_workspace_bytes(int B, int C, int H, int W1, int W2, int in_dtype) {
+  using namespace smoe;
+  if (!dtype_ok(in_dtype) || B < 0 || C < 0 || H < 0 || W1 < 0 || W2 < 0) return 0;
+  const int es = dtype_size(in_dtype);
+  int64_t bytes = 0;
+  const int p1 = padded_width(W1, es), p2 = padded_width(W2, es);
+  if (p1 != W1) bytes += ((int64_t)B * C * H * p1 * es + 255) / 256 * 256;
+  if (p2 != W2) bytes += ((int64_t)B * C * H * p2 * es + 255) / 256 * 256;
+  return bytes;
+}
+
+int smoe_corr_build(const void* fmap1, const void* fmap2, int in_dtype, int B, int C, int H, int W1,
+                    int W2, const smoe_pyramid_t* pyr, float scale, void* workspace,
+                    int64_t workspace_bytes, unsigned flags, smoe_stream_t stream) {
+  using namespace smoe;
+  if (int rc = validate_pyramid(pyr, "build")) return rc;
+  SMOE_REQUIRE(dtype_ok(in_dtype), SMOE_ERR_INVALID_ARG, "build: unknown input dtype %d", in_dtype);
+  SMOE_REQUIRE(B >= 0 && C >= 1 && H >= 0 && W1 >= 0 && W2 >= 0, SMOE_ERR_INVALID_ARG,
+               "build: bad dims B=%d C=%d H=%d W1=%d W2=%d", B, C, H, W1, W2);
+  SMOE_REQUIRE(pyr->B == B && pyr->H == H && pyr->W1 == W1 && pyr->width[0] == W2, SMOE_ERR_INVALID_ARG,
+               "build: pyramid dims (%d,%d,%d,W2=%d) do not match the feature maps (%d,%d,%d,W2=%d)",
+               pyr->B, pyr->H, pyr->W1, pyr->width[0], B, H, W1, W2);
+  for (int i = 1; i < pyr->num_levels; ++i)
+    SMOE_REQUIRE(pyr->width[i] == pyr->width[i - 1] / 2, SMOE_ERR_INVALID_ARG,
+                 "build: level %d width %d is not floor(%d/2)", i, pyr->width[i], pyr->width[i - 1]);
+  SMOE_REQUIRE(!(in_dtype == SMOE_DTYPE_F32 && pyr->dtype == SMOE_DTYPE_F16), SMOE_ERR_UNSUPPORTED,
+               "build: fp16 pyramid from fp32 feature maps is not part of the reference API");
+  if (B == 0 || H == 0 || W1 == 0 || W2 == 0) return SMOE_OK;
+  SMOE_REQUIRE(fmap1 && fmap2, SMOE_ERR_INVALID_ARG, "build: NULL feature map pointer");
+  SMOE_REQUIRE(aligned16(fmap1) && aligned16(fmap2), SMOE_ERR_INVALID_ARG,
+               "build: feature maps must be 16-byte aligned");
+  const int oes = dtype_size(pyr->dtype);
+  for (int i = 0; i < pyr->num_levels; ++i) {
+    const int per16 = 16 / oes;
+    SMOE_REQUIRE(aligned16(pyr->level_ptr[i]) && (pyr->pitch[i] * oes) % 16 == 0 &&
+                     ((int64_t)pyr->width[i] + per16 - 1) / per16 * per16 <= pyr->pitch[i],
+                 SMOE_ERR_INVALID_ARG,
+                 "build: level %d must be 16-byte aligned with a 16-byte-multiple pitch that holds the "
+                 "width rounded up to 16 bytes (use smoe_corr_pyramid_layout)", i);
+  }
+  SMOE_REQUIRE((long long)B * H * ((W1 + kBlockM - 1) / kBlockM) * ((W2 + kBlockN - 1) / kBlockN) <
+                   (1ll << 31),
+               SMOE_ERR_UNSUPPORTED, "build: too many work items");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int es = dtype_size(in_dtype);
+
+  // pitch-padded staging for W that violates TMA's 16-byte stride rule
+  const int p1 = padded_width(W1, es), p2 = padded_width(W2, es);
+  const void* a_base = fmap1;
+  const void* b_base = fmap2;
+  if (p1 != W1 || p2 != W2) {
+    const int64_t need = smoe_corr_build_workspace_bytes(B, C, H, W1, W2, in_dtype);
+    SMOE_REQUIRE(workspace != nullptr && workspace_bytes >= need && aligned16(workspace),
+                 SMOE_ERR_INVALID_ARG,
+                 "build: W1=%d/W2=%d need a %lld-byte 16-byte-aligned workspace (got %lld)", W1, W2,
+                 (long long)need, (long long)workspace_bytes);
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    const long long rows = (long long)B * C * H;
+    auto pad = [&](const void* src, int W, int Wp) -> const void* {
+      void* dst = ws;
+      const long long total = rows * Wp;
+      long long blocks = (total + 255) / 256;
+      if (blocks > 148ll * 16) blocks = 148ll * 16;
+      if (es == 4)
+        pad_rows_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(static_cast<const float*>(src),
+                                                               static_cast<float*>(dst), rows, W, Wp);
+      else
+        pad_rows_kernel<__half><<<(unsigned)blocks, 256, 0, st>>>(
+            static_cast<const __half*>(src), static_cast<__half*>(dst), rows, W, Wp);
+      ws += (rows * Wp * es + 255) / 256 * 256;
+      return dst;
+    };
+    if (p1 != W1) a_base = pad(fmap1, W1, p1);
+    if (p2 != W2) b_base = pad(fmap2, W2, p2);
+    if (int rc = check_launch("pad_rows_kernel")) return rc;
+  }
+
+  const bool tf32_round = (flags & SMOE_BUILD_TF32_TRUNCATE) == 0;
+  CUtensorMap ta, tb;
+  if (int rc = make_fmap_tmap(&ta, a_base, in_dtype, tf32_round, B, C, H, W1, p1)) return rc;
+  if (int rc = make_fmap_tmap(&tb, b_base, in_dtype, tf32_round, B, C, H, W2, p2)) return rc;
+
+  BuildDims dims;
+  dims.W1 = W1; dims.W2 = W2; dims.C = C; dims.H = H; dims.BH = B * H;
+  dims.MT = (W1 + kBlockM - 1) / kBlockM;
+  dims.NT = (W2 + kBlockN - 1) / kBlockN;
+  dims.scale = scale;
+  const PyrDev d = to_dev(pyr);
+  if (in_dtype == SMOE_DTYPE_F32) return launch_build<float, float>(ta, tb, d, dims, st);
+  if (pyr->dtype == SMOE_DTYPE_F16) return launch_build<__half, __half>(ta, tb, d, dims, st);
+  return launch_build<__half, float>(ta, tb, d, dims, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,125 @@
+// common.cuh -- error plumbing and small device helpers shared by the libsmoecorr kernels.
+#pragma once
+
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/smoe_corr.h"
+
+namespace smoe {
+
+// ---------------------------------------------------------------------------------- errors
+void set_error(const char* fmt, ...);   // thread-local message, defined in api.cu
+
+#define SMOE_REQUIRE(cond, code, ...)            \
+  do {                                           \
+    if (!(cond)) {                               \
+      ::smoe::set_error(__VA_ARGS__);            \
+      return (code);                             \
+    }                                            \
+  } while (0)
+
+#define SMOE_CUDA_OK(expr)                                                              \
+  do {                                                                                  \
+    cudaError_t err__ = (expr);                                                         \
+    if (err__ != cudaSuccess) {                                                         \
+      ::smoe::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__),      \
+                        __FILE__, __LINE__);                                            \
+      return SMOE_ERR_CUDA;                                                             \
+    }                                                                                   \
+  } while (0)
+
+inline int check_launch(const char* what) {
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) {
+    set_error("launch of %s failed: %s", what, cudaGetErrorString(err));
+    return SMOE_ERR_CUDA;
+  }
+  return SMOE_OK;
+}
+
+inline int dtype_size(int dtype) { return dtype == SMOE_DTYPE_F16 ? 2 : 4; }
+inline bool dtype_ok(int dtype) { return dtype == SMOE_DTYPE_F32 || dtype == SMOE_DTYPE_F16; }
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+int validate_pyramid(const smoe_pyramid_t* p, const char* who);   // api.cu
+
+// ------------------------------------------------------------------------------ device side
+// Kernel-side copy of the pyramid description (passed by value as a kernel parameter).
+struct PyrDev {
+  void* ptr[SMOE_MAX_LEVELS];
+  long long pitch[SMOE_MAX_LEVELS];
+  int width[SMOE_MAX_LEVELS];
+  int num_levels;
+};
+
+inline PyrDev to_dev(const smoe_pyramid_t* p) {
+  PyrDev d;
+  for (int i = 0; i < SMOE_MAX_LEVELS; ++i) {
+    d.ptr[i] = i < p->num_levels ? p->level_ptr[i] : nullptr;
+    d.pitch[i] = i < p->num_levels ? p->pitch[i] : 0;
+    d.width[i] = i < p->num_levels ? p->width[i] : 0;
+  }
+  d.num_levels = p->num_levels;
+  return d;
+}
+
+// 16-byte vector of volume elements -> floats
+template <typename T> struct Vec16;
+template <> struct Vec16<float> {
+  static constexpr int N = 4;
+  __device__ static void load(const float* p, float (&v)[4]) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+};
+template <> struct Vec16<__half> {
+  static constexpr int N = 8;
+  __device__ static void load(const __half* p, float (&v)[8]) {
+    const uint4 t = __ldg(reinterpret_cast<const uint4*>(p));
+    const __half2* h = reinterpret_cast<const __half2*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __half22float2(h[i]);
+      v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+  }
+};
+
+__device__ __forceinline__ float to_float(float v) { return v; }
+__device__ __forceinline__ float to_float(__half v) { return __half2float(v); }
+template <typename T> __device__ __forceinline__ T from_float(float v);
+template <> __device__ __forceinline__ float from_float<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half from_float<__half>(float v) { return __float2half_rn(v); }
+
+// Split a level coordinate into (base tap index, fractional weight).  Non-finite or
+// unrepresentably large coordinates are sent far out of range so that every tap is masked
+// (the reference's int cast of such values is undefined; all-zero is the defined behaviour here).
+__device__ __forceinline__ void split_coord(float xi, int radius, int& base, float& dx) {
+  float fl = floorf(xi);
+  dx = xi - fl;
+  if (!(fl > -1.0e8f && fl < 1.0e8f)) {   // also catches NaN
+    fl = -1.0e8f;
+    dx = 0.f;
+  }
+  base = static_cast<int>(fl) - radius;
+}
+
+// Interpolation in the reference's evaluation order (sampler_kernel.cu:46-59):
+//   out = 0; out += v0*(1-dx); out += v1*dx    (tap i=k first, then tap i=k+1)
+template <typename OT> __device__ __forceinline__ OT lerp_ref(float v0, float v1, float dx);
+template <> __device__ __forceinline__ float lerp_ref<float>(float v0, float v1, float dx) {
+  return fmaf(v1, dx, v0 * (1.0f - dx));
+}
+// scalar_t == c10::Half: every product and sum is computed in fp32 and rounded to half
+// (c10/util/Half-inl.h operators), weights are rounded to half first (scalar_t(dx)).
+template <> __device__ __forceinline__ __half lerp_ref<__half>(float v0, float v1, float dx) {
+  const float w1 = __half2float(__float2half_rn(1.0f - dx));
+  const float w0 = __half2float(__float2half_rn(dx));
+  const float a = __half2float(__float2half_rn(v0 * w1));
+  const float b = __half2float(__float2half_rn(v1 * w0));
+  return __float2half_rn(a + b);
+}
+
+}  // namespace smoe

@@ -1,0 +1,510 @@
+// lookup.cu -- pyramid lookup (forward), lookup backward and pyramid-gradient fold for sm_100a.
+//
+// These kernels are HBM/L2-bound gathers and scatters, not GEMMs.  Design:
+//  * forward, vector path: a group of 4 lanes owns one pixel; each lane fetches ONE aligned
+//    16-byte chunk of the (2r+2)-tap window of each level (all levels issued before any is
+//    used => 4 independent 16-B loads in flight per lane), neighbours exchange the chunk
+//    boundary value with one warp shuffle, interpolate, and the CTA transposes the 32-pixel x
+//    L*(2r+1) tile through shared memory so every global store is a full 128-byte line of one
+//    output channel (the output is channel-major, core/corr.py:146).
+//  * backward, accumulate: the mirror image -- the gradient tile is staged through shared
+//    memory with coalesced loads and each lane read-modify-writes the one 16-byte chunk it owns;
+//    rows are pixel-private, so no atomics are needed (as in sampler_kernel.cu:102).
+//  * backward, overwrite: one pass writes every element of the dense gradient (zeros outside the
+//    window), replacing the reference's zeros_like + scatter pair (sampler_kernel.cu:148-163).
+//  * generic scalar kernels cover unaligned widths / pitches and radii other than 4.
+#include "common.cuh"
+
+namespace smoe {
+
+constexpr int kTilePx = 32;       // pixels per CTA tile (one 128-byte line of fp32 outputs)
+constexpr int kFwdThreads = 128;  // 4 lanes per pixel
+
+// ----------------------------------------------------------------------------- forward (vector)
+template <typename VT, typename OT, int R, int NL>
+__global__ void __launch_bounds__(kFwdThreads)
+lookup_fwd_vec_kernel(PyrDev pyr, const float* __restrict__ coords, long long coords_bstride,
+                      float coord_scale, OT* __restrict__ out, int HW) {
+  constexpr int EPL = Vec16<VT>::N;          // elements per 16-byte chunk
+  constexpr int LOG_EPL = (EPL == 4) ? 2 : 3;
+  constexpr int RD = 2 * R + 1;
+  static_assert(EPL - 1 + 2 * R + 2 <= 4 * EPL, "window must fit the 4 chunks of a lane group");
+  __shared__ OT s_out[NL * RD][kTilePx + 1];
+
+  const int tid = threadIdx.x;
+  const int p = tid >> 2, q = tid & 3;
+  const int b = blockIdx.y;
+  const int hw0 = blockIdx.x * kTilePx;
+  const int hw = hw0 + p;
+  const bool valid = hw < HW;
+  const float x0 = valid ? __ldg(coords + (long long)b * coords_bstride + hw) * coord_scale : 0.f;
+  const long long row = (long long)b * HW + hw;
+
+  float v[NL][EPL];
+  int sh[NL];
+  float dxs[NL];
+  float lscale = 1.0f;
+#pragma unroll
+  for (int l = 0; l < NL; ++l) {
+    int base;
+    split_coord(x0 * lscale, R, base, dxs[l]);
+    lscale *= 0.5f;
+    const int s = base & (EPL - 1);
+    const int ci = (base >> LOG_EPL) + q;          // arithmetic shift == floor division
+    sh[l] = s;
+    const int width = pyr.width[l];
+    const int nchunks = (width + EPL - 1) >> LOG_EPL;
+    const bool need = valid && (q * EPL < s + 2 * R + 2) && ci >= 0 && ci < nchunks;
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) v[l][j] = 0.f;
+    if (need) {
+      const VT* src = static_cast<const VT*>(pyr.ptr[l]) + row * pyr.pitch[l] + (long long)ci * EPL;
+      Vec16<VT>::load(src, v[l]);
+      if ((ci + 1) * EPL > width) {                // tail chunk: mask elements >= width
+#pragma unroll
+        for (int j = 0; j < EPL; ++j)
+          if (ci * EPL + j >= width) v[l][j] = 0.f;
+      }
+    }
+  }
+#pragma unroll
+  for (int l = 0; l < NL; ++l) {
+    const float nxt = __shfl_down_sync(0xffffffffu, v[l][0], 1);   // first element of chunk q+1
+    const float dx = dxs[l];
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) {
+      const float v1 = (j + 1 < EPL) ? v[l][j + 1] : nxt;
+      const OT e = lerp_ref<OT>(v[l][j], v1, dx);
+      const int k = q * EPL + j - sh[l];
+      if (k >= 0 && k < RD) s_out[l * RD + k][p] = e;
+    }
+  }
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31;
+  if (hw0 + lane < HW) {
+    OT* dst = out + (long long)b * (NL * RD) * HW + hw0 + lane;
+#pragma unroll 4
+    for (int c = warp; c < NL * RD; c += kFwdThreads / 32) dst[(long long)c * HW] = s_out[c][lane];
+  }
+}
+
+// ---------------------------------------------------------------------------- forward (generic)
+template <typename VT, typename OT>
+__global__ void __launch_bounds__(128)
+lookup_fwd_generic_kernel(PyrDev pyr, const float* __restrict__ coords, long long coords_bstride,
+                          float coord_scale, int R, OT* __restrict__ out, int HW) {
+  const int hw = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (hw >= HW) return;
+  const int RD = 2 * R + 1;
+  const float x0 = __ldg(coords + (long long)b * coords_bstride + hw) * coord_scale;
+  const long long row = (long long)b * HW + hw;
+  float lscale = 1.0f;
+  for (int l = 0; l < pyr.num_levels; ++l) {
+    int base;
+    float dx;
+    split_coord(x0 * lscale, R, base, dx);
+    lscale *= 0.5f;
+    const int width = pyr.width[l];
+    const VT* src = static_cast<const VT*>(pyr.ptr[l]) + row * pyr.pitch[l];
+    OT* dst = out + ((long long)b * pyr.num_levels * RD + (long long)l * RD) * HW + hw;
+    float prev = (base >= 0 && base < width) ? to_float(src[base]) : 0.f;
+    for (int k = 0; k < RD; ++k) {
+      const int i1 = base + k + 1;
+      const float nxt = (i1 >= 0 && i1 < width) ? to_float(src[i1]) : 0.f;
+      dst[(long long)k * HW] = lerp_ref<OT>(prev, nxt, dx);
+      prev = nxt;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------ backward contributions
+// Gradient reaching window element t (0..2r+1) of a pixel, in the reference's order
+// (sampler_kernel.cu:92-102): g = 0; g += grad[t-1]*dx (t>0); g += grad[t]*(1-dx) (t<2r+1).
+template <typename VT> struct BwdTap;
+template <> struct BwdTap<float> {
+  __device__ static float eval(float gm1, float g0, bool has_m1, bool has_0, float dx) {
+    float g = has_m1 ? gm1 * dx : 0.f;
+    if (has_0) g = fmaf(g0, 1.0f - dx, g);
+    return g;
+  }
+};
+template <> struct BwdTap<__half> {   // c10::Half arithmetic: fp32 op, round to half after each
+  __device__ static float eval(float gm1, float g0, bool has_m1, bool has_0, float dx) {
+    const float w0 = __half2float(__float2half_rn(dx));
+    const float w1 = __half2float(__float2half_rn(1.0f - dx));
+    float g = 0.f;
+    if (has_m1) g = __half2float(__float2half_rn(g + __half2float(__float2half_rn(gm1 * w0))));
+    if (has_0) g = __half2float(__float2half_rn(g + __half2float(__float2half_rn(g0 * w1))));
+    return g;
+  }
+};
+
+// -------------------------------------------------------------------- backward accumulate (vector)
+template <typename GT, int R, int NL>
+__global__ void __launch_bounds__(kFwdThreads)
+lookup_bwd_acc_vec_kernel(PyrDev gp, const float* __restrict__ coords, long long coords_bstride,
+                          float coord_scale, const GT* __restrict__ gout, int HW) {
+  constexpr int EPL = 4, LOG_EPL = 2;
+  constexpr int RD = 2 * R + 1;
+  __shared__ float s_g[NL * RD][kTilePx + 1];
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.y;
+  const int hw0 = blockIdx.x * kTilePx;
+  {
+    const bool ok = hw0 + lane < HW;
+    const GT* src = gout + (long long)b * (NL * RD) * HW + hw0 + lane;
+#pragma unroll 4
+    for (int c = warp; c < NL * RD; c += kFwdThreads / 32)
+      s_g[c][lane] = ok ? to_float(src[(long long)c * HW]) : 0.f;
+  }
+  __syncthreads();
+
+  const int p = tid >> 2, q = tid & 3;
+  const int hw = hw0 + p;
+  if (hw >= HW) return;
+  const float x0 = __ldg(coords + (long long)b * coords_bstride + hw) * coord_scale;
+  const long long row = (long long)b * HW + hw;
+  float lscale = 1.0f;
+#pragma unroll
+  for (int l = 0; l < NL; ++l) {
+    int base;
+    float dx;
+    split_coord(x0 * lscale, R, base, dx);
+    lscale *= 0.5f;
+    const int s = base & (EPL - 1);
+    const int ci = (base >> LOG_EPL) + q;
+    const int width = gp.width[l];
+    const int nchunks = (width + EPL - 1) >> LOG_EPL;
+    if (!((q * EPL < s + 2 * R + 2) && ci >= 0 && ci < nchunks)) continue;
+    float4* dst = reinterpret_cast<float4*>(static_cast<float*>(gp.ptr[l]) + row * gp.pitch[l] +
+                                            (long long)ci * EPL);
+    float4 cur = *dst;
+    float* c4 = reinterpret_cast<float*>(&cur);
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) {
+      const int t = q * EPL + j - s;
+      if (t >= 0 && t <= RD && ci * EPL + j < width) {
+        const float gm1 = (t > 0) ? s_g[l * RD + t - 1][p] : 0.f;
+        const float g0 = (t < RD) ? s_g[l * RD + t][p] : 0.f;
+        c4[j] += BwdTap<float>::eval(gm1, g0, t > 0, t < RD, dx);
+      }
+    }
+    *dst = cur;
+  }
+}
+
+// ------------------------------------------------------------------- backward accumulate (generic)
+template <typename GT>
+__global__ void __launch_bounds__(128)
+lookup_bwd_acc_generic_kernel(PyrDev gp, const float* __restrict__ coords, long long coords_bstride,
+                              float coord_scale, int R, const GT* __restrict__ gout, int HW) {
+  const int hw = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (hw >= HW) return;
+  const int RD = 2 * R + 1;
+  const float x0 = __ldg(coords + (long long)b * coords_bstride + hw) * coord_scale;
+  const long long row = (long long)b * HW + hw;
+  float lscale = 1.0f;
+  for (int l = 0; l < gp.num_levels; ++l) {
+    int base;
+    float dx;
+    split_coord(x0 * lscale, R, base, dx);
+    lscale *= 0.5f;
+    const int width = gp.width[l];
+    float* dst = static_cast<float*>(gp.ptr[l]) + row * gp.pitch[l];
+    const GT* g = gout + ((long long)b * gp.num_levels * RD + (long long)l * RD) * HW + hw;
+    float gm1 = 0.f;
+    for (int t = 0; t <= RD; ++t) {
+      const float g0 = (t < RD) ? to_float(g[(long long)t * HW]) : 0.f;
+      const int idx = base + t;
+      if (idx >= 0 && idx < width) dst[idx] += BwdTap<float>::eval(gm1, g0, t > 0, t < RD, dx);
+      gm1 = g0;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------ backward overwrite (dense)
+// One CTA stages the gradients of 32 consecutive pixels, then each warp writes whole gradient
+// rows (zeros outside the 2r+2 window).  VEC = elements per store (16 bytes when aligned, else 1).
+constexpr int kDenseThreads = 256;
+
+template <typename VT, typename GT, int VEC>
+__global__ void __launch_bounds__(kDenseThreads)
+lookup_bwd_dense_kernel(PyrDev gp, const float* __restrict__ coords, long long coords_bstride,
+                        float coord_scale, int R, const GT* __restrict__ gout, int HW) {
+  extern __shared__ float s_dyn[];   // [NL*RD][kTilePx+1] gradients, then [kTilePx] coords
+  const int RD = 2 * R + 1;
+  const int NC = gp.num_levels * RD;
+  float* s_x = s_dyn + NC * (kTilePx + 1);
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.y;
+  const int hw0 = blockIdx.x * kTilePx;
+  {
+    const bool ok = hw0 + lane < HW;
+    const GT* src = gout + (long long)b * NC * HW + hw0 + lane;
+    for (int c = warp; c < NC; c += kDenseThreads / 32)
+      s_dyn[c * (kTilePx + 1) + lane] = ok ? to_float(src[(long long)c * HW]) : 0.f;
+    if (warp == 0)
+      s_x[lane] = ok ? __ldg(coords + (long long)b * coords_bstride + hw0 + lane) * coord_scale : 0.f;
+  }
+  __syncthreads();
+  for (int p = warp; p < kTilePx; p += kDenseThreads / 32) {
+    const int hw = hw0 + p;
+    if (hw >= HW) break;
+    const long long row = (long long)b * HW + hw;
+    float lscale = 1.0f;
+    for (int l = 0; l < gp.num_levels; ++l) {
+      int base;
+      float dx;
+      split_coord(s_x[p] * lscale, R, base, dx);
+      lscale *= 0.5f;
+      const int width = gp.width[l];
+      VT* dst = static_cast<VT*>(gp.ptr[l]) + row * gp.pitch[l];
+      const float* g = s_dyn + (l * RD) * (kTilePx + 1) + p;
+      for (int i0 = lane * VEC; i0 < width; i0 += 32 * VEC) {
+        VT vals[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          const int t = i0 + j - base;
+          float gv = 0.f;
+          if (t >= 0 && t <= RD) {
+            const float gm1 = (t > 0) ? g[(t - 1) * (kTilePx + 1)] : 0.f;
+            const float g0 = (t < RD) ? g[t * (kTilePx + 1)] : 0.f;
+            gv = BwdTap<VT>::eval(gm1, g0, t > 0, t < RD, dx);
+          }
+          vals[j] = from_float<VT>(gv);
+        }
+        if (VEC == 1) {
+          dst[i0] = vals[0];
+        } else {
+          *reinterpret_cast<uint4*>(dst + i0) = *reinterpret_cast<const uint4*>(vals);
+        }
+      }
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------- fold
+// G0[j] += 0.5*(G1[j/2] + 0.5*(G2[j/4] + 0.5*G3[j/8])), stopping at the first level whose index
+// falls outside its width (the column an odd level dropped, core/corr.py:124).
+__global__ void __launch_bounds__(256)
+fold_grad_kernel(PyrDev gp, long long rows) {
+  const int w0 = gp.width[0];
+  const long long total = rows * w0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / w0;
+    const int j = static_cast<int>(i - row * w0);
+    int top = 0;
+    for (int l = 1; l < gp.num_levels; ++l) {
+      if ((j >> l) >= gp.width[l]) break;
+      top = l;
+    }
+    if (top == 0) continue;
+    float t = 0.f;
+    for (int l = top; l >= 1; --l) {
+      const float gl = static_cast<const float*>(gp.ptr[l])[row * gp.pitch[l] + (j >> l)];
+      t = gl + 0.5f * t;
+    }
+    float* g0 = static_cast<float*>(gp.ptr[0]) + row * gp.pitch[0] + j;
+    *g0 += 0.5f * t;
+  }
+}
+
+// --------------------------------------------------------------------------------- dispatch
+static bool vec_ok(const smoe_pyramid_t* p) {
+  const int es = dtype_size(p->dtype);
+  for (int i = 0; i < p->num_levels; ++i) {
+    if (!aligned16(p->level_ptr[i])) return false;
+    if ((p->pitch[i] * es) % 16 != 0) return false;
+    const int per16 = 16 / es;
+    // a tail chunk may be read/written whole: it must stay inside the row
+    if (((int64_t)p->width[i] + per16 - 1) / per16 * per16 > p->pitch[i]) return false;
+  }
+  return true;
+}
+
+template <typename VT, typename OT, int NL>
+static void launch_fwd_vec(const PyrDev& d, const float* coords, long long cbs, float cs, void* out,
+                           int HW, int B, cudaStream_t st) {
+  dim3 grid((HW + kTilePx - 1) / kTilePx, B);
+  lookup_fwd_vec_kernel<VT, OT, 4, NL><<<grid, kFwdThreads, 0, st>>>(d, coords, cbs, cs,
+                                                                    static_cast<OT*>(out), HW);
+}
+
+template <typename VT, typename OT>
+static void dispatch_fwd_vec(int NL, const PyrDev& d, const float* coords, long long cbs, float cs,
+                             void* out, int HW, int B, cudaStream_t st) {
+  switch (NL) {
+    case 1: launch_fwd_vec<VT, OT, 1>(d, coords, cbs, cs, out, HW, B, st); break;
+    case 2: launch_fwd_vec<VT, OT, 2>(d, coords, cbs, cs, out, HW, B, st); break;
+    case 3: launch_fwd_vec<VT, OT, 3>(d, coords, cbs, cs, out, HW, B, st); break;
+    default: launch_fwd_vec<VT, OT, 4>(d, coords, cbs, cs, out, HW, B, st); break;
+  }
+}
+
+template <typename GT, int NL>
+static void launch_bwd_acc_vec(const PyrDev& d, const float* coords, long long cbs, float cs,
+                               const void* gout, int HW, int B, cudaStream_t st) {
+  dim3 grid((HW + kTilePx - 1) / kTilePx, B);
+  lookup_bwd_acc_vec_kernel<GT, 4, NL><<<grid, kFwdThreads, 0, st>>>(
+      d, coords, cbs, cs, static_cast<const GT*>(gout), HW);
+}
+
+template <typename GT>
+static void dispatch_bwd_acc_vec(int NL, const PyrDev& d, const float* coords, long long cbs,
+                                 float cs, const void* gout, int HW, int B, cudaStream_t st) {
+  switch (NL) {
+    case 1: launch_bwd_acc_vec<GT, 1>(d, coords, cbs, cs, gout, HW, B, st); break;
+    case 2: launch_bwd_acc_vec<GT, 2>(d, coords, cbs, cs, gout, HW, B, st); break;
+    case 3: launch_bwd_acc_vec<GT, 3>(d, coords, cbs, cs, gout, HW, B, st); break;
+    default: launch_bwd_acc_vec<GT, 4>(d, coords, cbs, cs, gout, HW, B, st); break;
+  }
+}
+
+template <typename VT, typename GT>
+static int launch_bwd_dense(const smoe_pyramid_t* gp, const PyrDev& d, const float* coords,
+                            long long cbs, float cs, int R, const void* gout, int HW, int B,
+                            cudaStream_t st) {
+  dim3 grid((HW + kTilePx - 1) / kTilePx, B);
+  const size_t smem = ((size_t)gp->num_levels * (2 * R + 1) * (kTilePx + 1) + kTilePx) * sizeof(float);
+  SMOE_REQUIRE(smem <= 48 * 1024, SMOE_ERR_UNSUPPORTED, "lookup_bwd: radius %d too large", R);
+  constexpr int VEC = 16 / sizeof(VT);
+  bool vec = vec_ok(gp);
+  for (int i = 0; i < gp->num_levels; ++i) vec = vec && (gp->width[i] % VEC == 0);
+  if (vec)
+    lookup_bwd_dense_kernel<VT, GT, VEC><<<grid, kDenseThreads, smem, st>>>(
+        d, coords, cbs, cs, R, static_cast<const GT*>(gout), HW);
+  else
+    lookup_bwd_dense_kernel<VT, GT, 1><<<grid, kDenseThreads, smem, st>>>(
+        d, coords, cbs, cs, R, static_cast<const GT*>(gout), HW);
+  return SMOE_OK;
+}
+
+}  // namespace smoe
+
+extern "C" {
+
+int smoe_corr_lookup(const smoe_pyramid_t* pyr, const float* coords, int64_t coords_batch_stride,
+                     float coord_scale, int radius, void* out, int out_dtype,
+                     smoe_stream_t stream) {
+  using namespace smoe;
+  if (int rc = validate_pyramid(pyr, "lookup")) return rc;
+  SMOE_REQUIRE(radius >= 0 && radius <= 64, SMOE_ERR_INVALID_ARG, "lookup: radius %d outside [0,64]",
+               radius);
+  SMOE_REQUIRE(dtype_ok(out_dtype), SMOE_ERR_INVALID_ARG, "lookup: unknown out dtype %d", out_dtype);
+  SMOE_REQUIRE(!(pyr->dtype == SMOE_DTYPE_F32 && out_dtype == SMOE_DTYPE_F16), SMOE_ERR_UNSUPPORTED,
+               "lookup: fp16 output from an fp32 pyramid is not part of the reference API");
+  const long long HW = (long long)pyr->H * pyr->W1;
+  if (pyr->B == 0 || HW == 0) return SMOE_OK;
+  SMOE_REQUIRE(coords && out, SMOE_ERR_INVALID_ARG, "lookup: NULL coords/out pointer");
+  SMOE_REQUIRE(coords_batch_stride >= HW, SMOE_ERR_INVALID_ARG,
+               "lookup: coords batch stride %lld < H*W1 %lld", (long long)coords_batch_stride, HW);
+  SMOE_REQUIRE(pyr->B <= 65535, SMOE_ERR_UNSUPPORTED, "lookup: batch %d > 65535", pyr->B);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const PyrDev d = to_dev(pyr);
+  const bool f16v = pyr->dtype == SMOE_DTYPE_F16, f16o = out_dtype == SMOE_DTYPE_F16;
+  if (radius == 4 && vec_ok(pyr)) {
+    if (!f16v)
+      dispatch_fwd_vec<float, float>(pyr->num_levels, d, coords, coords_batch_stride, coord_scale,
+                                     out, (int)HW, pyr->B, st);
+    else if (f16o)
+      dispatch_fwd_vec<__half, __half>(pyr->num_levels, d, coords, coords_batch_stride, coord_scale,
+                                       out, (int)HW, pyr->B, st);
+    else
+      dispatch_fwd_vec<__half, float>(pyr->num_levels, d, coords, coords_batch_stride, coord_scale,
+                                      out, (int)HW, pyr->B, st);
+  } else {
+    dim3 grid((unsigned)((HW + 127) / 128), pyr->B);
+    if (!f16v)
+      lookup_fwd_generic_kernel<float, float><<<grid, 128, 0, st>>>(
+          d, coords, coords_batch_stride, coord_scale, radius, static_cast<float*>(out), (int)HW);
+    else if (f16o)
+      lookup_fwd_generic_kernel<__half, __half><<<grid, 128, 0, st>>>(
+          d, coords, coords_batch_stride, coord_scale, radius, static_cast<__half*>(out), (int)HW);
+    else
+      lookup_fwd_generic_kernel<__half, float><<<grid, 128, 0, st>>>(
+          d, coords, coords_batch_stride, coord_scale, radius, static_cast<float*>(out), (int)HW);
+  }
+  return check_launch("lookup forward");
+}
+
+int smoe_corr_lookup_bwd(const smoe_pyramid_t* gp, const float* coords, int64_t coords_batch_stride,
+                         float coord_scale, int radius, const void* grad_out, int grad_out_dtype,
+                         int mode, smoe_stream_t stream) {
+  using namespace smoe;
+  if (int rc = validate_pyramid(gp, "lookup_bwd")) return rc;
+  SMOE_REQUIRE(radius >= 0 && radius <= 64, SMOE_ERR_INVALID_ARG,
+               "lookup_bwd: radius %d outside [0,64]", radius);
+  SMOE_REQUIRE(dtype_ok(grad_out_dtype), SMOE_ERR_INVALID_ARG, "lookup_bwd: unknown grad dtype %d",
+               grad_out_dtype);
+  SMOE_REQUIRE(mode == SMOE_BWD_OVERWRITE || mode == SMOE_BWD_ACCUMULATE, SMOE_ERR_INVALID_ARG,
+               "lookup_bwd: unknown mode %d", mode);
+  const long long HW = (long long)gp->H * gp->W1;
+  if (gp->B == 0 || HW == 0) return SMOE_OK;
+  SMOE_REQUIRE(coords && grad_out, SMOE_ERR_INVALID_ARG, "lookup_bwd: NULL coords/grad pointer");
+  SMOE_REQUIRE(coords_batch_stride >= HW, SMOE_ERR_INVALID_ARG,
+               "lookup_bwd: coords batch stride %lld < H*W1 %lld", (long long)coords_batch_stride, HW);
+  SMOE_REQUIRE(gp->B <= 65535, SMOE_ERR_UNSUPPORTED, "lookup_bwd: batch %d > 65535", gp->B);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const PyrDev d = to_dev(gp);
+  const bool f16g = grad_out_dtype == SMOE_DTYPE_F16;
+  if (mode == SMOE_BWD_ACCUMULATE) {
+    SMOE_REQUIRE(gp->dtype == SMOE_DTYPE_F32, SMOE_ERR_UNSUPPORTED,
+                 "lookup_bwd: the accumulating gradient pyramid must be fp32");
+    if (radius == 4 && vec_ok(gp)) {
+      if (f16g)
+        dispatch_bwd_acc_vec<__half>(gp->num_levels, d, coords, coords_batch_stride, coord_scale,
+                                     grad_out, (int)HW, gp->B, st);
+      else
+        dispatch_bwd_acc_vec<float>(gp->num_levels, d, coords, coords_batch_stride, coord_scale,
+                                    grad_out, (int)HW, gp->B, st);
+    } else {
+      dim3 grid((unsigned)((HW + 127) / 128), gp->B);
+      if (f16g)
+        lookup_bwd_acc_generic_kernel<__half><<<grid, 128, 0, st>>>(
+            d, coords, coords_batch_stride, coord_scale, radius,
+            static_cast<const __half*>(grad_out), (int)HW);
+      else
+        lookup_bwd_acc_generic_kernel<float><<<grid, 128, 0, st>>>(
+            d, coords, coords_batch_stride, coord_scale, radius,
+            static_cast<const float*>(grad_out), (int)HW);
+    }
+  } else {
+    int rc;
+    if (gp->dtype == SMOE_DTYPE_F16) {
+      SMOE_REQUIRE(f16g, SMOE_ERR_UNSUPPORTED,
+                   "lookup_bwd: an fp16 gradient volume needs an fp16 upstream gradient");
+      rc = launch_bwd_dense<__half, __half>(gp, d, coords, coords_batch_stride, coord_scale, radius,
+                                            grad_out, (int)HW, gp->B, st);
+    } else if (f16g) {
+      rc = launch_bwd_dense<float, __half>(gp, d, coords, coords_batch_stride, coord_scale, radius,
+                                           grad_out, (int)HW, gp->B, st);
+    } else {
+      rc = launch_bwd_dense<float, float>(gp, d, coords, coords_batch_stride, coord_scale, radius,
+                                          grad_out, (int)HW, gp->B, st);
+    }
+    if (rc) return rc;
+  }
+  return check_launch("lookup backward");
+}
+
+int smoe_corr_fold_pyramid_grad(const smoe_pyramid_t* gp, smoe_stream_t stream) {
+  using namespace smoe;
+  if (int rc = validate_pyramid(gp, "fold_pyramid_grad")) return rc;
+  SMOE_REQUIRE(gp->dtype == SMOE_DTYPE_F32, SMOE_ERR_UNSUPPORTED,
+               "fold_pyramid_grad: gradient pyramid must be fp32");
+  const long long rows = (long long)gp->B * gp->H * gp->W1;
+  if (rows == 0 || gp->width[0] == 0 || gp->num_levels == 1) return SMOE_OK;
+  const long long total = rows * gp->width[0];
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148ll * 32) blocks = 148ll * 32;
+  fold_grad_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(to_dev(gp), rows);
+  return check_launch("fold_pyramid_grad");
+}
+
+}  // extern "C"

@@ -1,0 +1,55 @@
+"""Make an unmodified reference checkout use this implementation.
+
+The reference binds the names by value (``from core.corr import CorrBlock1D, ...`` in
+core/SMoEStereo.py:7 and core/raft_stereo.py:6) and selects one by
+``args.corr_implementation`` (core/SMoEStereo.py:211-221), and core/corr.py:5-8 does a bare
+``import corr_sampler``.  ``install()`` therefore
+  1. registers this package's ``corr_sampler`` module under that top-level name, and
+  2. rebinds the four class names in every already-imported reference module that holds them.
+No reference file is edited.
+"""
+from __future__ import annotations
+
+import sys
+
+from . import corr as _corr
+from . import corr_sampler as _sampler
+
+_NAMES = ("CorrBlock1D", "CorrBlockFast1D", "PytorchAlternateCorrBlock1D", "CorrSampler")
+_TARGETS = ("core.corr", "core.raft_stereo", "core.SMoEStereo")
+_saved: dict = {}
+
+
+def install(modules=_TARGETS) -> list[str]:
+    """Returns the list of 'module.name' bindings that were replaced."""
+    replaced = []
+    if sys.modules.get("corr_sampler") is not _sampler:
+        _saved[("sys.modules", "corr_sampler")] = sys.modules.get("corr_sampler")
+        sys.modules["corr_sampler"] = _sampler
+        replaced.append("sys.modules.corr_sampler")
+    for mname in modules:
+        mod = sys.modules.get(mname)
+        if mod is None:
+            continue
+        for n in _NAMES:
+            if hasattr(mod, n) and getattr(mod, n) is not getattr(_corr, n):
+                _saved[(mname, n)] = getattr(mod, n)
+                setattr(mod, n, getattr(_corr, n))
+                replaced.append(f"{mname}.{n}")
+        if hasattr(mod, "corr_sampler") and mod.corr_sampler is not _sampler:
+            _saved[(mname, "corr_sampler")] = mod.corr_sampler
+            mod.corr_sampler = _sampler
+            replaced.append(f"{mname}.corr_sampler")
+    return replaced
+
+
+def uninstall() -> None:
+    for (mname, n), old in list(_saved.items()):
+        if mname == "sys.modules":
+            if old is None:
+                sys.modules.pop(n, None)
+            else:
+                sys.modules[n] = old
+        elif mname in sys.modules:
+            setattr(sys.modules[mname], n, old)
+        del _saved[(mname, n)]

@@ -1,0 +1,123 @@
+"""GPU parity: lookup backward (accumulating fused kernel, dense corr_sampler.backward API),
+pyramid-gradient fold, and the full autograd path of CorrBlock1D against the reference's own
+autograd results (golden vectors) and the CPU oracle."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_names, load_golden, rel_max
+
+pytestmark = pytest.mark.gpu
+
+GRAD_TOL = 5e-5      # same arithmetic in fp32 (reference path goes through grid_sample backward)
+E2E_GRAD_TOL = 1e-3  # includes the tf32 volume and cuBLAS einsum backward
+
+
+@pytest.fixture(scope="module")
+def sb():
+    import smoe_stereo_b200 as m
+    assert torch.cuda.is_available()
+    return m
+
+
+def _bwd_acc(sb, gp, coords, gout, r):
+    from smoe_stereo_b200 import _lib
+    from smoe_stereo_b200.corr import _stream_ptr
+    rc = _lib.lib().smoe_corr_lookup_bwd(gp.ref, coords.data_ptr(), coords.stride(0), 1.0, r,
+                                         gout.data_ptr(), _lib.DTYPE_F32, _lib.BWD_ACCUMULATE,
+                                         _stream_ptr(gp.device))
+    _lib.check(rc, "lookup_bwd")
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_lookup_bwd_accumulate_and_fold_vs_golden(sb, name):
+    from gpu_util import dev
+    from smoe_stereo_b200 import _lib
+    from smoe_stereo_b200.corr import _stream_ptr
+    g = load_golden(name)
+    d = g["dims"]
+    gp = sb.FusedPyramid(d["B"], d["H"], d["W1"], d["W2"], d["L"], torch.float32, dev(), zero=True)
+    for t in range(d["T"]):
+        _bwd_acc(sb, gp, torch.from_numpy(g["coords"][t]).to(dev()),
+                 torch.from_numpy(g["gout"][t]).to(dev()), d["r"])
+    for i in range(d["L"]):
+        assert rel_max(gp.level(i).cpu().numpy(), g[f"glvl{i}"]) < GRAD_TOL
+    # padding columns were never touched
+    used = torch.zeros(gp.pitch, dtype=torch.bool)
+    for i in range(d["L"]):
+        used[gp.offsets[i]:gp.offsets[i] + gp.widths[i]] = True
+    assert torch.all(gp.buffer[:, ~used.to(dev())] == 0)
+    # fold onto level 0 == avg_pool2d backward chain
+    from oracle import corr_oracle
+    want = corr_oracle.numpy_fold_pyramid_grad([g[f"glvl{i}"] for i in range(d["L"])])
+    _lib.check(_lib.lib().smoe_corr_fold_pyramid_grad(gp.ref, _stream_ptr(gp.device)), "fold")
+    assert rel_max(gp.level(0).cpu().numpy(), want) < GRAD_TOL
+
+
+@pytest.mark.parametrize("name", ["odd37", "c256_w40", "r3_l3"])
+def test_corr_sampler_backward_api(sb, oracle, name):
+    """Dense single-pass gradient == zeros_like + scatter (sampler_kernel.cu:138-166)."""
+    from gpu_util import dev
+    g = load_golden(name)
+    d = g["dims"]
+    rd = 2 * d["r"] + 1
+    for i in range(d["L"]):
+        vol = torch.from_numpy(np.ascontiguousarray(g[f"lvl{i}"])).to(dev())
+        c = np.ascontiguousarray(g["coords"][0][:, :1] / np.float32(2 ** i))
+        go = np.ascontiguousarray(g["gout"][0][:, i * rd:(i + 1) * rd])
+        want = oracle.c_lookup_level_bwd(c, go, vol.shape[-1], d["r"])
+        got, = sb.corr_sampler.backward(vol, torch.from_numpy(c).to(dev()),
+                                        torch.from_numpy(go).to(dev()), d["r"])
+        assert got.shape == vol.shape and got.dtype == vol.dtype
+        assert rel_max(got.cpu().numpy(), want) < 2e-6
+        # and through the CorrSampler autograd.Function (core/corr.py:17-29)
+        v2 = vol.clone().requires_grad_(True)
+        out = sb.CorrSampler.apply(v2, torch.from_numpy(c).to(dev()), d["r"])
+        out.backward(torch.from_numpy(go).to(dev()))
+        assert rel_max(v2.grad.cpu().numpy(), want) < 2e-6
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_corrblock_autograd_vs_reference(sb, name):
+    """d loss / d fmap through build + T lookups equals the reference's autograd (golden df1/df2)."""
+    from gpu_util import dev
+    g = load_golden(name)
+    d = g["dims"]
+    f1 = torch.from_numpy(g["f1"]).to(dev()).requires_grad_(True)
+    f2 = torch.from_numpy(g["f2"]).to(dev()).requires_grad_(True)
+    blk = sb.CorrBlock1D(f1, f2, num_levels=d["L"], radius=d["r"])
+    loss = 0.0
+    for t in range(d["T"]):
+        out = blk(torch.from_numpy(g["coords"][t]).to(dev()))
+        assert out.requires_grad
+        loss = loss + (out * torch.from_numpy(g["gout"][t]).to(dev())).sum()
+    loss.backward()
+    assert rel_max(f1.grad.cpu().numpy(), g["df1"]) < E2E_GRAD_TOL
+    assert rel_max(f2.grad.cpu().numpy(), g["df2"]) < E2E_GRAD_TOL
+    assert blk._state.grad_pyr is None     # persistent gradient pyramid released after use
+
+
+def test_bwd_linearity_and_adjoint_full_size(sb):
+    """Size-independent properties at BASELINE config-2 shape (B=8, 80x184): the backward is the
+    exact adjoint of the forward (<out, gout> == <pyramid, grad_pyramid>) and is linear."""
+    from gpu_util import dev, make_coords
+    from smoe_stereo_b200.corr import _lookup
+    B, H, W = 8, 80, 184
+    gen = torch.Generator(device="cpu").manual_seed(1)
+    pyr = sb.FusedPyramid(B, H, W, W, 4, torch.float32, dev(), zero=True)
+    for i in range(4):
+        pyr.level(i).copy_(torch.randn(B, H, W, pyr.widths[i], generator=gen).to(dev()))
+    coords = torch.from_numpy(make_coords(B, H, W, W, 1, seed=3)[0]).to(dev())
+    gout = torch.randn(B, 36, H, W, generator=gen).to(dev())
+    out = _lookup(pyr, coords, 4, torch.float32)
+    gp = sb.FusedPyramid(B, H, W, W, 4, torch.float32, dev(), zero=True)
+    _bwd_acc(sb, gp, coords, gout, 4)
+    lhs = (out.double() * gout.double()).sum().item()
+    rhs = sum((pyr.level(i).double() * gp.level(i).double()).sum().item() for i in range(4))
+    assert abs(lhs - rhs) <= 1e-6 * max(abs(lhs), 1.0) + 1e-3
+    gp2 = sb.FusedPyramid(B, H, W, W, 4, torch.float32, dev(), zero=True)
+    _bwd_acc(sb, gp2, coords, 2 * gout, 4)
+    _bwd_acc(sb, gp, coords, gout, 4)          # accumulate twice == once with 2x
+    assert torch.equal(gp.buffer, gp2.buffer)

@@ -1,0 +1,133 @@
+"""GPU parity: tcgen05/TMA volume + fused pyramid build against the reference's golden vectors
+and the CPU oracle.  Tolerance: north_star's <=1e-3 relative (max|d|/max|ref|) for the
+tensor-core path; measured values are printed so the run log records the actual error."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_names, load_golden, rel_l2, rel_max
+
+pytestmark = pytest.mark.gpu
+
+VOL_TOL = 1e-3          # north_star tolerance for the tf32 tensor-core path
+EXACT_TOL = 3e-6        # fp16-valued inputs are exact in tf32/f16 operands; fp32 accumulate only
+
+
+@pytest.fixture(scope="module")
+def sb():
+    import smoe_stereo_b200 as m
+    assert torch.cuda.is_available()
+    return m
+
+
+def _levels(blk):
+    return [lv.squeeze(3).float().cpu().numpy() for lv in blk.corr_pyramid]
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_build_vs_reference_golden(sb, name):
+    from gpu_util import dev
+    g = load_golden(name)
+    d = g["dims"]
+    f1 = torch.from_numpy(g["f1"]).to(dev())
+    f2 = torch.from_numpy(g["f2"]).to(dev())
+    blk = sb.CorrBlock1D(f1, f2, num_levels=d["L"], radius=d["r"])
+    lv = _levels(blk)
+    tol = EXACT_TOL if name.startswith("fp16_valued") else VOL_TOL
+    for i in range(d["L"]):
+        assert lv[i].shape == g[f"lvl{i}"].shape
+        e = rel_max(lv[i], g[f"lvl{i}"])
+        print(f"[build {name}] level {i}: rel_max={e:.3e} rel_l2={rel_l2(lv[i], g[f'lvl{i}']):.3e}")
+        assert e < tol
+    # pooling is exact given level 0: (a+b)/2 in fp32, floor-halving of odd widths
+    for i in range(1, d["L"]):
+        w = lv[i].shape[-1]
+        np.testing.assert_array_equal(lv[i], (lv[i - 1][..., 0:2 * w:2] + lv[i - 1][..., 1:2 * w:2]) * np.float32(0.5))
+    # and the lookups on top of it agree with the reference end to end
+    for t in range(d["T"]):
+        out = blk(torch.from_numpy(g["coords"][t]).to(dev()))
+        assert out.dtype == torch.float32
+        assert rel_max(out.cpu().numpy(), g["out"][t]) < tol
+    v = sb.CorrBlock1D.corr(f1, f2)
+    assert tuple(v.shape) == (d["B"], d["H"], d["W1"], 1, d["W2"])
+    assert rel_max(v.squeeze(3).cpu().numpy(), g["vol"]) < tol
+
+
+@pytest.mark.parametrize("shape", [
+    (1, 256, 135, 240, 240),    # BASELINE config 1 (540x960 at 1/4 res)
+    (2, 256, 24, 184, 184),     # config 2 width (320x736), 2 M tiles with a 56-row tail
+    (1, 256, 8, 312, 312),      # config 3 width (384x1248): 3 M tiles, 2 N tiles
+    (1, 256, 3, 750, 750),      # config 4 width (W%4 != 0 -> padded staging), 6 M x 3 N tiles
+    (1, 100, 2, 72, 520),       # C not a multiple of the K stage, W1 != W2, 3 N tiles
+])
+def test_build_shapes_vs_oracle(sb, oracle, shape):
+    from gpu_util import dev
+    B, C, H, W1, W2 = shape
+    rs = np.random.RandomState(B * 1000 + W1)
+    f1 = rs.standard_normal((B, C, H, W1)).astype(np.float32)
+    f2 = rs.standard_normal((B, C, H, W2)).astype(np.float32)
+    want = oracle.c_pyramid(oracle.c_corr_volume(f1, f2), 4)
+    blk = sb.CorrBlock1D(torch.from_numpy(f1).to(dev()), torch.from_numpy(f2).to(dev()))
+    lv = _levels(blk)
+    for i in range(4):
+        e = rel_max(lv[i], want[i])
+        print(f"[build {shape}] level {i}: rel_max={e:.3e} rel_l2={rel_l2(lv[i], want[i]):.3e}")
+        assert e < VOL_TOL
+
+
+def test_build_fp16_valued_inputs_are_exact(sb, oracle):
+    """Default mixed_precision=True feeds fp16-valued feature maps up-cast to fp32
+    (core/SMoEStereo.py:168,213): tf32 operands then carry them exactly."""
+    from gpu_util import dev
+    rs = np.random.RandomState(5)
+    f1 = rs.standard_normal((1, 256, 4, 240)).astype(np.float16).astype(np.float32)
+    f2 = rs.standard_normal((1, 256, 4, 240)).astype(np.float16).astype(np.float32)
+    want = oracle.numpy_corr_volume(f1, f2)
+    blk = sb.CorrBlock1D(torch.from_numpy(f1).to(dev()), torch.from_numpy(f2).to(dev()))
+    assert rel_max(_levels(blk)[0], want) < EXACT_TOL
+
+
+def test_tf32_modes_error_report(sb, oracle):
+    """Record the error of both tf32 operand modes (TMA TFLOAT32 conversion vs MMA truncation)."""
+    from gpu_util import dev
+    from smoe_stereo_b200 import _lib
+    from smoe_stereo_b200.corr import _build_into
+    rs = np.random.RandomState(9)
+    f1 = rs.standard_normal((1, 256, 8, 240)).astype(np.float32)
+    f2 = rs.standard_normal((1, 256, 8, 240)).astype(np.float32)
+    want = oracle.numpy_corr_volume(f1, f2)
+    t1, t2 = torch.from_numpy(f1).to(dev()), torch.from_numpy(f2).to(dev())
+    for flags, label in ((0, "tma_tfloat32"), (_lib.BUILD_TF32_TRUNCATE, "mma_truncate")):
+        pyr = sb.FusedPyramid(1, 8, 240, 240, 4, torch.float32, dev())
+        _build_into(pyr, t1, t2, flags)
+        got = pyr.level(0).cpu().numpy()
+        bias = float(np.sum(got.astype(np.float64) * want) / np.sum(want.astype(np.float64) ** 2) - 1)
+        print(f"[tf32 {label}] rel_max={rel_max(got, want):.3e} rel_l2={rel_l2(got, want):.3e} "
+              f"scale_bias={bias:+.3e}")
+        assert rel_max(got, want) < VOL_TOL
+
+
+def test_build_batch_independent_and_deterministic(sb):
+    """Each (b,h) unit is independent: building a batch equals building its items one by one,
+    bit for bit -- the property batch/row sharding relies on."""
+    from gpu_util import dev
+    g = torch.Generator(device="cpu").manual_seed(0)
+    f1 = torch.randn(3, 64, 5, 96, generator=g).to(dev())
+    f2 = torch.randn(3, 64, 5, 96, generator=g).to(dev())
+    full = sb.CorrBlock1D(f1, f2)._state.pyr.buffer.clone()
+    again = sb.CorrBlock1D(f1, f2)._state.pyr.buffer
+    rows = 5 * 96
+    for i in range(4):
+        pass
+    pyr = sb.CorrBlock1D(f1, f2)._state.pyr
+    for b in range(3):
+        one = sb.CorrBlock1D(f1[b:b + 1].contiguous(), f2[b:b + 1].contiguous())._state.pyr
+        for i in range(4):
+            assert torch.equal(one.level(i)[0], pyr.level(i)[b])
+    for i in range(4):
+        lvl = slice(pyr.offsets[i], pyr.offsets[i] + pyr.widths[i])
+        assert torch.equal(full[:, lvl], again[:, lvl])
+    # row shard == rows of the full build
+    top = sb.CorrBlock1D(f1[:, :, :2].contiguous(), f2[:, :, :2].contiguous())._state.pyr
+    for i in range(4):
+        assert torch.equal(top.level(i), pyr.level(i)[:, :2])

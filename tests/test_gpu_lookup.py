@@ -1,0 +1,107 @@
+"""GPU parity: lookup forward (fused multi-level kernel and the corr_sampler.forward API)
+against the golden vectors of the reference and against the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_names, load_golden, rel_max
+
+pytestmark = pytest.mark.gpu
+
+LOOKUP_TOL = 5e-5   # reference goes through grid_sample's normalise round trip (utils.py:84-99)
+ORACLE_TOL = 2e-6   # same formula, fp32, fma contraction only
+
+
+@pytest.fixture(scope="module")
+def sb():
+    import smoe_stereo_b200 as m
+    assert torch.cuda.is_available()
+    return m
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_fused_lookup_vs_reference_golden(sb, name):
+    from gpu_util import dev, fused_from_levels
+    from smoe_stereo_b200.corr import _lookup
+    g = load_golden(name)
+    d = g["dims"]
+    pyr = fused_from_levels([g[f"lvl{i}"] for i in range(d["L"])])
+    for t in range(d["T"]):
+        coords = torch.from_numpy(g["coords"][t]).to(dev())
+        out = _lookup(pyr, coords, d["r"], torch.float32)
+        assert out.shape == g["out"][t].shape and out.is_contiguous()
+        assert rel_max(out.cpu().numpy(), g["out"][t]) < LOOKUP_TOL
+
+
+@pytest.mark.parametrize("name", ["odd37", "c256_w40", "w1_ne_w2"])
+def test_corr_sampler_forward_api(sb, oracle, name):
+    """Planar single-level volumes, pre-scaled coords, as CorrBlockFast1D drives the op
+    (core/corr.py:44-51).  W2=37 exercises the unaligned scalar kernel, 40 the vector one."""
+    from gpu_util import dev
+    g = load_golden(name)
+    d = g["dims"]
+    for i in range(d["L"]):
+        vol = np.ascontiguousarray(g[f"lvl{i}"])
+        for t in range(d["T"]):
+            c = np.ascontiguousarray(g["coords"][t][:, :1] / np.float32(2 ** i))
+            want = oracle.c_lookup([vol], c, d["r"])
+            got, = sb.corr_sampler.forward(torch.from_numpy(vol).to(dev()),
+                                           torch.from_numpy(c).to(dev()), d["r"])
+            assert got.dtype == torch.float32 and tuple(got.shape) == want.shape
+            assert rel_max(got.cpu().numpy(), want) < ORACLE_TOL
+
+
+def test_corr_sampler_errors(sb):
+    from gpu_util import dev
+    vol = torch.zeros(1, 2, 8, 8, device=dev())
+    coords = torch.zeros(1, 1, 2, 8, device=dev())
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        sb.corr_sampler.forward(vol.cpu(), coords, 4)
+    with pytest.raises(RuntimeError, match="must be contiguous"):
+        sb.corr_sampler.forward(vol.permute(0, 1, 3, 2), coords, 4)
+    with pytest.raises(RuntimeError):
+        sb.corr_sampler.forward(vol, coords[:, :, :1], 4)
+
+
+def test_lookup_cfg1_full_size_vs_oracle(sb, oracle):
+    """BASELINE config 1 pixel grid (B=1,H=135,W=240), 4 levels, radius 4, random pyramid."""
+    from gpu_util import dev, fused_from_levels, make_coords
+    from smoe_stereo_b200.corr import _lookup
+    B, H, W = 1, 135, 240
+    rs = np.random.RandomState(7)
+    lv0 = rs.standard_normal((B, H, W, W)).astype(np.float32)
+    levels = oracle.c_pyramid(lv0, 4)
+    pyr = fused_from_levels(levels)
+    coords = make_coords(B, H, W, W, 3, seed=11)
+    for t in range(3):
+        want = oracle.c_lookup(levels, np.ascontiguousarray(coords[t]), 4)
+        got = _lookup(pyr, torch.from_numpy(coords[t]).to(dev()), 4, torch.float32)
+        assert rel_max(got.cpu().numpy(), want) < ORACLE_TOL
+    # single-channel coords are accepted too (reference op takes (B,1,H,W))
+    got1 = _lookup(pyr, torch.from_numpy(coords[0][:, :1].copy()).to(dev()), 4, torch.float32)
+    assert torch.equal(got1, _lookup(pyr, torch.from_numpy(coords[0]).to(dev()), 4, torch.float32))
+
+
+def test_lookup_ragged_and_nonfinite(sb, oracle):
+    """H*W not a multiple of the 32-pixel tile, B>1, NaN/inf/huge coordinates -> zeros."""
+    from gpu_util import dev, fused_from_levels
+    from smoe_stereo_b200.corr import _lookup
+    B, H, W1, W2 = 3, 5, 13, 48
+    rs = np.random.RandomState(3)
+    levels = oracle.c_pyramid(rs.standard_normal((B, H, W1, W2)).astype(np.float32), 4)
+    pyr = fused_from_levels(levels)
+    coords = rs.uniform(-20, W2 + 20, size=(B, 2, H, W1)).astype(np.float32)
+    coords[0, 0, 0, :4] = [np.nan, np.inf, -np.inf, 3e9]
+    want = oracle.c_lookup(levels, coords, 4)
+    got = _lookup(pyr, torch.from_numpy(coords).to(dev()), 4, torch.float32).cpu().numpy()
+    assert np.all(np.isfinite(got))
+    assert np.all(got[0, :, 0, :4] == 0)
+    assert rel_max(got, want) < ORACLE_TOL
+
+
+def test_lookup_empty(sb):
+    from gpu_util import dev
+    from smoe_stereo_b200.corr import _lookup
+    pyr = sb.FusedPyramid(0, 4, 8, 16, 4, torch.float32, dev())
+    out = _lookup(pyr, torch.zeros(0, 2, 4, 8, device=dev()), 4, torch.float32)
+    assert tuple(out.shape) == (0, 36, 4, 8)

@@ -1,0 +1,73 @@
+"""CPU: host-side mirror of the reference interface -- argument checks, drop-in installation,
+shard arithmetic.  No CUDA calls."""
+import sys
+import types
+
+import pytest
+import torch
+
+import smoe_stereo_b200 as sb
+from smoe_stereo_b200 import sharding
+
+
+def test_blocks_refuse_cpu_tensors_loudly():
+    f = torch.zeros(1, 8, 2, 8)
+    for cls in (sb.CorrBlock1D, sb.CorrBlockFast1D, sb.PytorchAlternateCorrBlock1D):
+        with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+            cls(f, f, num_levels=4, radius=4)
+    with pytest.raises(RuntimeError, match="volume must be a CUDA tensor"):
+        sb.corr_sampler.forward(torch.zeros(1, 2, 8, 8), torch.zeros(1, 1, 2, 8), 4)
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        sb.corr_sampler.backward(torch.zeros(1, 2, 8, 8), torch.zeros(1, 1, 2, 8),
+                                 torch.zeros(1, 9, 2, 8), 4)
+    with pytest.raises(NotImplementedError):       # dead in the reference too (core/corr.py:161)
+        sb.AlternateCorrBlock(f, f)
+
+
+def test_reference_signatures():
+    import inspect
+    for cls in (sb.CorrBlock1D, sb.CorrBlockFast1D, sb.PytorchAlternateCorrBlock1D):
+        ps = list(inspect.signature(cls.__init__).parameters.values())
+        assert [p.name for p in ps] == ["self", "fmap1", "fmap2", "num_levels", "radius"]
+        assert ps[3].default == 4 and ps[4].default == 4
+        assert callable(cls.corr)
+    assert [p for p in inspect.signature(sb.corr_sampler.forward).parameters] == \
+        ["volume", "coords", "radius"]
+    assert [p for p in inspect.signature(sb.corr_sampler.backward).parameters] == \
+        ["volume", "coords", "corr_grad", "radius"]
+
+
+def test_install_rebinds_reference_modules():
+    fake = types.ModuleType("core.raft_stereo")
+    fake.CorrBlock1D = object
+    fake.CorrBlockFast1D = object
+    fake.PytorchAlternateCorrBlock1D = object
+    sys.modules["core.raft_stereo"] = fake
+    try:
+        done = sb.install()
+        assert "core.raft_stereo.CorrBlock1D" in done
+        assert fake.CorrBlock1D is sb.CorrBlock1D and fake.CorrBlockFast1D is sb.CorrBlockFast1D
+        import corr_sampler            # the bare import of core/corr.py:5-8 now resolves to ours
+        assert corr_sampler is sb.corr_sampler
+        sb.uninstall()
+        assert fake.CorrBlock1D is object and "corr_sampler" not in sys.modules
+    finally:
+        sys.modules.pop("core.raft_stereo", None)
+        sb.uninstall()
+
+
+def test_shard_bounds():
+    assert [sharding.shard_bounds(500, 8, r) for r in range(8)] == \
+        [(0, 63), (63, 126), (126, 189), (189, 252), (252, 314), (314, 376), (376, 438), (438, 500)]
+    assert sharding.shard_sizes(8, 8) == [1] * 8
+    assert sharding.shard_sizes(3, 4) == [1, 1, 1, 0]
+    for n in (0, 1, 7, 135, 500):
+        for w in (1, 2, 4, 8):
+            b = [sharding.shard_bounds(n, w, r) for r in range(w)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+    with pytest.raises(ValueError):
+        sharding.shard_bounds(4, 2, 2)
+    t = torch.arange(2 * 3 * 5 * 4).view(2, 3, 5, 4)
+    assert torch.equal(sharding.take_shard(t, "rows", 2, 1), t[:, :, 3:])
+    assert torch.equal(sharding.take_shard(t, "batch", 2, 0), t[:1])
