@@ -1,0 +1,421 @@
+#!/usr/bin/env python
+"""bench.py -- correlation hot path benchmark (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg1]
+
+metric  : "corr build + 32-iter lookup pairs/sec at 540x960" (BASELINE.json configs[0]:
+          B=1, C=256, H=135, W=240, 4 levels, radius 4, 32 lookup iterations).
+step    : one pass of the hot path over one stereo pair: volume+pyramid build (1 tcgen05 kernel)
+          + 32 fused pyramid lookups (32 kernels), i.e. 33 launches of our own kernels.
+value   : pairs/s with inputs resident in HBM, the step replayed as a CUDA graph, timed with CUDA
+          events on the launching stream; steps rotate over several independent input sets whose
+          combined footprint exceeds the 126 MB L2 (stated in config.l2).
+e2e     : pairs/s through the public API (CorrBlock1D(...) + __call__) with HOST buffers: pinned
+          host feature maps / coords copied H2D and every lookup result copied D2H inside the
+          timed region.
+roofline: the lookup kernel (dominant: 32 of 33 launches) -- algorithmic bytes per launch
+          (px * 308 B) / average launch duration measured with CUDA events.
+cpu_baseline / --impl reference: the oracle's C port of the reference's CPU path, timed on the
+          host cores of the same box (reported baseline only).
+
+Under torchrun (N>1) every rank runs the same per-GPU workload (weak scaling, batch-partitioned
+pairs, no collective in the path); the time is the max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: B, C, H, W, levels, radius, iters, description
+    "cfg1": dict(B=1, C=256, H=135, W=240, L=4, r=4, iters=32,
+                 desc="540x960 pair at 1/4 res: B=1,C=256,H=135,W=240, 4 levels, radius 4, 32 lookups"),
+    "cfg3": dict(B=8, C=256, H=96, W=312, L=4, r=4, iters=32,
+                 desc="KITTI 384x1248, B=8: C=256,H=96,W=312, 4 levels, radius 4, 32 lookups"),
+    "cfg1x8": dict(B=8, C=256, H=135, W=240, L=4, r=4, iters=32,
+                   desc="8 x 540x960 pairs per step: B=8,C=256,H=135,W=240, 4 levels, radius 4, 32 lookups"),
+}
+METRIC = "corr build+32-iter lookup pairs/sec at 540x960"
+UNIT = "pairs/s"
+
+
+def level_widths(w, L):
+    out = []
+    for _ in range(L):
+        out.append(w)
+        w //= 2
+    return out
+
+
+def algorithmic_bytes(wl, vol_bytes=4, in_bytes=4):
+    """build = read each fmap once + write each used level once;
+    lookup per iteration = px * (4 + L*(2r+2)*s_vol + L*(2r+1)*4)."""
+    px = wl["B"] * wl["H"] * wl["W"]
+    build = 2 * wl["B"] * wl["C"] * wl["H"] * wl["W"] * in_bytes + px * sum(level_widths(wl["W"], wl["L"])) * vol_bytes
+    lookup = px * (4 + wl["L"] * (2 * wl["r"] + 2) * vol_bytes + wl["L"] * (2 * wl["r"] + 1) * 4)
+    flops = 2 * wl["C"] * px * wl["W"]
+    return build, lookup, flops
+
+
+def synth_inputs(wl, seed):
+    """Synthetic feature maps and per-iteration coordinates: smooth disparity +
+    noise growing with the iteration, >=1% of pixels out of range on each side."""
+    rs = np.random.RandomState(seed)
+    B, C, H, W = wl["B"], wl["C"], wl["H"], wl["W"]
+    f1 = rs.standard_normal((B, C, H, W)).astype(np.float32)
+    f2 = rs.standard_normal((B, C, H, W)).astype(np.float32)
+    xs = np.broadcast_to(np.arange(W, dtype=np.float32), (B, H, W))
+    ys = np.broadcast_to(np.arange(H, dtype=np.float32)[:, None], (B, H, W))
+    base = rs.uniform(0, 64, size=(B, H, 1)).astype(np.float32)
+    coords = np.empty((wl["iters"], B, 2, H, W), dtype=np.float32)
+    for t in range(wl["iters"]):
+        x = xs - base - rs.standard_normal((B, H, W)).astype(np.float32) * (0.5 * t)
+        m = rs.uniform(size=x.shape)
+        x = np.where(m < 0.015, -rs.uniform(1, 30, size=x.shape), x)
+        x = np.where(m > 0.985, W + rs.uniform(0, 30, size=x.shape), x)
+        coords[t, :, 0] = x.astype(np.float32)
+        coords[t, :, 1] = ys
+    return f1, f2, coords
+
+
+# ----------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:           # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def window(self, t0, t1):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            if ts < t0 - 0.15 or ts > t1 + 0.15:
+                continue
+            parts = [p.strip() for p in line.split(",")]
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+
+
+# ------------------------------------------------------------------------------- CPU baseline
+def cpu_path_timer(wl, budget_s, min_runs=2):
+    """Time the oracle's C port of the reference's CPU path (build + iters lookups)."""
+    from oracle import corr_oracle as o
+    o.build()
+    f1, f2, coords = synth_inputs(wl, seed=0)
+    base = o.CorrPathBaseline(wl["B"], wl["C"], wl["H"], wl["W"], wl["W"], wl["L"], wl["r"], wl["iters"])
+    base.run(f1, f2, coords)            # warm-up (page faults, thread pool)
+    times = []
+    t_start = time.perf_counter()
+    while len(times) < min_runs or (time.perf_counter() - t_start < budget_s and len(times) < 200):
+        t0 = time.perf_counter()
+        base.run(f1, f2, coords)
+        times.append(time.perf_counter() - t0)
+    return times, o.num_threads()
+
+
+def run_reference_arm(args, wl, rank, world):
+    """--impl reference: the reference's CPU implementation of the path (oracle C port, all host
+    threads) on the same config/metric.  Rank 0 only."""
+    if rank != 0:
+        return
+    from oracle import corr_oracle as o
+    o.build()
+    f1, f2, coords = synth_inputs(wl, seed=0)
+    base = o.CorrPathBaseline(wl["B"], wl["C"], wl["H"], wl["W"], wl["W"], wl["L"], wl["r"], wl["iters"])
+    for _ in range(max(args.warmup, 1)):
+        base.run(f1, f2, coords)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        base.run(f1, f2, coords)
+    dt = time.perf_counter() - t0
+    val = args.steps * wl["B"] / dt
+    cores = o.num_threads()
+    sample = f"{args.steps} full steps of {args.workload} (build + {wl['iters']} lookups each), C port of core/corr.py"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": wl["desc"], "device": "host CPU"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg1", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU baseline sampling")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sets", type=int, default=0, help="independent input sets to rotate over")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    wl = WORKLOADS[args.workload]
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, wl, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import smoe_stereo_b200 as sb
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+
+    B, C, H, W, L, r, iters = (wl[k] for k in ("B", "C", "H", "W", "L", "r", "iters"))
+    build_bytes, lookup_bytes, build_flops = algorithmic_bytes(wl)
+    pitch = sb._lib.pyramid_layout(W, L, sb._lib.DTYPE_F32)[2]
+    set_bytes = 2 * B * C * H * W * 4 + B * H * W * pitch * 4 + iters * B * 2 * H * W * 4
+    nsets = args.sets or max(2, int(np.ceil(3 * 126e6 / set_bytes)) + 1)
+    nsets = min(nsets, 8)
+
+    # ---- resident inputs + one captured CUDA graph per input set
+    sets = []
+    host = []
+    for s in range(nsets):
+        f1, f2, coords = synth_inputs(wl, seed=1000 * rank + s)
+        host.append((f1, f2, coords))
+        sets.append((torch.from_numpy(f1).to(dev), torch.from_numpy(f2).to(dev),
+                     torch.from_numpy(coords).to(dev)))
+    torch.cuda.synchronize()
+
+    def step_eager(f1, f2, coords):
+        blk = sb.CorrBlock1D(f1, f2, num_levels=L, radius=r)
+        out = None
+        for t in range(iters):
+            out = blk(coords[t])
+        return blk, out
+
+    side = torch.cuda.Stream(dev)
+    graphs = []
+    with torch.cuda.stream(side):
+        for s in range(nsets):
+            step_eager(*sets[s])                    # warm the allocator / module outside capture
+        torch.cuda.synchronize()
+        for s in range(nsets):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                keep = step_eager(*sets[s])
+            graphs.append((g, keep))
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: K graph-replayed steps, device-timed
+    stream = torch.cuda.current_stream(dev)
+    for i in range(args.warmup):
+        graphs[i % nsets][0].replay()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    wall0 = time.time()
+    e0.record(stream)
+    for i in range(args.steps):
+        graphs[i % nsets][0].replay()
+    e1.record(stream)
+    barrier()
+    wall1 = time.time()
+    dev_s = e0.elapsed_time(e1) / 1e3
+    if world > 1:
+        t = torch.tensor([dev_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_s = float(t.item())
+    value = world * args.steps * B / dev_s
+
+    # ---- per-kernel durations (CUDA events on the launching stream, same rotation over sets)
+    def time_kernel(fn, reps):
+        for i in range(5):
+            fn(i)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for i in range(reps):
+            fn(i)
+        b.record(stream)
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / 1e3 / reps
+
+    from smoe_stereo_b200.corr import _build_into, _lookup
+    pyrs = [g[1][0]._state.pyr for g in graphs]
+
+    # graph of `iters` lookups only / build only: kernel time without host launch gaps
+    def capture(fn):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            fn()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g, stream=side):
+                keep = fn()
+        return g, keep
+
+    lk_graphs = [capture(lambda s=s: [_lookup(pyrs[s], sets[s][2][t], r, torch.float32) for t in range(iters)])
+                 for s in range(nsets)]
+    bd_graphs = [capture(lambda s=s: _build_into(pyrs[s], sets[s][0], sets[s][1])) for s in range(nsets)]
+    t_lookup = time_kernel(lambda i: lk_graphs[i % nsets][0].replay(), 50) / iters
+    t_build = time_kernel(lambda i: bd_graphs[i % nsets][0].replay(), 100)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:           # noqa: BLE001
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
+    tf_peak = float(peaks.get("bf16_tflops", 1590.0)) / 2.0     # tf32 = half the bf16 rate
+
+    def roof(bytes_, secs, traffic=None):
+        ach = bytes_ / secs / 1e9
+        return {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                "traffic": traffic, "us_per_launch": secs * 1e6, "algorithmic_bytes": bytes_, "peak_source": peak_src}
+
+    roofline = roof(lookup_bytes, t_lookup)
+    roofline["kernel"] = "lookup_fwd_vec_kernel<float,float,4,4>"
+    roofline["note"] = ("pyramid of this workload (%.0f MB) fits the 126 MB L2: bandwidth is L2-assisted and the "
+                        "kernel is launch/latency-bound at this size" % (B * H * W * pitch * 4 / 1e6)
+                        if B * H * W * pitch * 4 < 126e6 else "pyramid exceeds L2: HBM-bound")
+    roofline_build = roof(build_bytes, t_build)
+    roofline_build["kernel"] = "corr_build_kernel<float,float>"
+    roofline_build["tensor_tflops"] = build_flops / t_build / 1e12
+    roofline_build["tensor_frac_of_tf32_peak"] = build_flops / t_build / 1e12 / tf_peak
+
+    # ---- e2e: public API, host buffers, H2D + D2H inside the timed region
+    pin = [(torch.from_numpy(h[0]).pin_memory(), torch.from_numpy(h[1]).pin_memory(),
+            torch.from_numpy(h[2]).pin_memory()) for h in host[:2]]
+    out_host = [torch.empty((iters, B, L * (2 * r + 1), H, W), dtype=torch.float32).pin_memory() for _ in range(2)]
+    copy_stream = torch.cuda.Stream(dev)
+
+    def step_e2e(i):
+        hf1, hf2, hc = pin[i % 2]
+        oh = out_host[i % 2]
+        f1 = hf1.to(dev, non_blocking=True)
+        f2 = hf2.to(dev, non_blocking=True)
+        c = hc.to(dev, non_blocking=True)
+        blk = sb.CorrBlock1D(f1, f2, num_levels=L, radius=r)
+        for t in range(iters):
+            out = blk(c[t])
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(ev)
+                oh[t].copy_(out, non_blocking=True)
+                out.record_stream(copy_stream)
+        stream.wait_stream(copy_stream)
+
+    e2e_steps = max(3, min(args.steps, 200))
+    for i in range(3):
+        step_e2e(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        step_e2e(i)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    h2d = 2 * B * C * H * W * 4 + iters * B * 2 * H * W * 4
+    d2h = iters * B * L * (2 * r + 1) * H * W * 4
+    e2e = {"value": world * e2e_steps * B / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+           "how": "CorrBlock1D(...) + 32 x __call__ from pinned host buffers; all 32 lookup results copied to host"}
+
+    # ---- eager (non-graph) API throughput, inputs resident
+    def eager(i):
+        step_eager(*sets[i % nsets])
+    t_eager = time_kernel(eager, 50)
+
+    clocks = sampler.window(wall0, wall1) if sampler else None
+    if sampler:
+        sampler.stop()
+
+    # ---- CPU baseline (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        times, cores = cpu_path_timer(WORKLOADS[args.workload], args.cpu_budget)
+        best = min(times)
+        cpu = {"value": wl["B"] / statistics.median(times), "unit": UNIT, "cores": cores, "kind": "port",
+               "best": wl["B"] / best, "runs": len(times),
+               "sample": f"{len(times)} full steps of {args.workload} (build + {iters} lookups), oracle C port "
+                         f"(OpenMP, {cores} threads), median"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "tf32 (fp32 in/out, fp32 accumulate)",
+            "data": "synthetic",
+            "config": {"workload": wl["desc"], "per_gpu_batch": B, "partitioning": f"batch x{world}, no collective",
+                       "l2": f"steps rotate over {nsets} independent input sets ({nsets * set_bytes / 1e6:.0f} MB > 126 MB L2)",
+                       "launch": "one CUDA graph per step (1 build + 32 lookup kernels)"},
+            "e2e": e2e, "gpu_launches": args.steps * (1 + iters),
+            "roofline": roofline, "roofline_build": roofline_build,
+            "cpu_baseline": cpu, "clocks": clocks,
+            "eager_api_pairs_per_s": B / t_eager,
+            "breakdown_us": {"build": t_build * 1e6, "lookup_per_iter": t_lookup * 1e6,
+                             "sum_build_plus_iters": (t_build + iters * t_lookup) * 1e6,
+                             "graph_step": 1e6 * dev_s / args.steps},
+            "wall_s": wall1 - wall0,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -100,16 +100,18 @@ int64_t smoe_corr_build_workspace_bytes(int B, int C, int H, int W1, int W2, int
 
 /*
  * Correlation volume + pyramid:
- *   level0[(b,h,w1), w2] = scale * sum_c fmap1[b,c,h,w1] * fmap2[b,c,h,w2]
+ *   level0[(b,h,w1), w2] = (sum_c fmap1[b,c,h,w1] * fmap2[b,c,h,w2]) / denom     (denom = sqrt(C))
  *   level(i+1)[., j]     = (level i[., 2j] + level i[., 2j+1]) / 2,  j < floor(W2_i/2)
  * computed on tcgen05 tensor cores (kind::tf32 for fp32 inputs, kind::f16 for fp16 inputs,
  * fp32 accumulation in TMEM), operands staged by TMA, scale and pooling fused in the epilogue.
  * pyr->dtype is the output type (fp32, or fp16 when the inputs are fp16 -- the reference's
  * reg_cuda path under autocast; each fp16 level is pooled from the rounded previous level, as
- * F.avg_pool2d on a half tensor does).
+ * F.avg_pool2d on a half tensor does).  The division is a true fp32 division as in
+ * core/corr.py:156 (for fp16 outputs it is applied to the fp16-rounded sum, as the reference's
+ * fp16 einsum output is).
  */
 int smoe_corr_build(const void* fmap1, const void* fmap2, int in_dtype, int B, int C, int H,
-                    int W1, int W2, const smoe_pyramid_t* pyr, float scale, void* workspace,
+                    int W1, int W2, const smoe_pyramid_t* pyr, float denom, void* workspace,
                     int64_t workspace_bytes, unsigned flags, smoe_stream_t stream);
 
 /*

@@ -103,7 +103,7 @@ def _build_into(pyr: FusedPyramid, fmap1: torch.Tensor, fmap2: torch.Tensor, fla
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=fmap1.device) if ws_bytes else None
     with _on_device(fmap1.device):
         rc = L.smoe_corr_build(fmap1.data_ptr(), fmap2.data_ptr(), code, B, C, H, W1, W2, pyr.ref,
-                               1.0 / math.sqrt(C), ws.data_ptr() if ws is not None else None,
+                               math.sqrt(C), ws.data_ptr() if ws is not None else None,
                                ws_bytes, flags, _stream_ptr(fmap1.device))
     _lib.check(rc, "smoe_corr_build")
     if ws is not None:

@@ -1,6 +1,6 @@
 // build.cu -- all-pairs 1-D correlation volume + fused W-axis pyramid on tcgen05 / TMA (sm_100a).
 //
-//   level0[(b,h,w1), w2] = scale * sum_c f1[b,c,h,w1] * f2[b,c,h,w2]          (core/corr.py:148-156)
+//   level0[(b,h,w1), w2] = (sum_c f1[b,c,h,w1] * f2[b,c,h,w2]) / sqrt(C)       (core/corr.py:148-156)
 //   level(i+1)[., j]     = (level i[., 2j] + level i[., 2j+1]) / 2            (core/corr.py:122-125)
 //
 // For a fixed (b,h) this is a [W1 x C] * [C x W2] GEMM whose operands are both "MN-major": in NCHW
@@ -18,6 +18,7 @@
 //               in registers (pooling runs along N == along a thread's own TMEM row), store all
 //               levels.  Accumulators are double buffered so this overlaps the next item's MMAs.
 #include <cuda.h>
+#include <math.h>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -56,7 +57,19 @@ template <> struct OperandCfg<__half> {
 struct BuildDims {
   int W1, W2, C, H, BH;      // BH = B*H image rows
   int MT, NT;                // tiles per image row
-  float scale;
+  float denom;               // level0 = sum / denom   (core/corr.py:156: corr / sqrt(D))
+  float rcp;                 // 1/denom, used when it is exact (denom a power of two)
+  int rcp_exact;
+};
+
+// Division exactly as the reference performs it: a true fp32 division, replaced by the (bit-
+// identical) multiplication when the denominator is a power of two (C = 64, 256, ...).
+struct Scaler {
+  float denom, rcp;
+  int exact;
+  __device__ __forceinline__ float operator()(float x) const {
+    return exact ? x * rcp : __fdiv_rn(x, denom);
+  }
 };
 
 // ------------------------------------------------------------------------------------ epilogue
@@ -67,10 +80,10 @@ template <typename OT> struct ChunkStore;
 
 template <> struct ChunkStore<float> {
   __device__ static void run(const uint32_t (&acc)[32], const PyrDev& pyr, long long row, int n0,
-                             float scale, bool row_valid) {
+                             const Scaler& sc, bool row_valid) {
     float v[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) * scale;
+    for (int j = 0; j < 32; ++j) v[j] = sc(__uint_as_float(acc[j]));
     if (!row_valid) return;
     {
       float* dst = static_cast<float*>(pyr.ptr[0]) + row * pyr.pitch[0] + n0;
@@ -128,10 +141,11 @@ template <> struct ChunkStore<__half> {
   }
   __device__ static float rh(float x) { return __half2float(__float2half_rn(x)); }
   __device__ static void run(const uint32_t (&acc)[32], const PyrDev& pyr, long long row, int n0,
-                             float scale, bool row_valid) {
+                             const Scaler& sc, bool row_valid) {
     float v[32];
+    // the reference's einsum output is already fp16; the division then rounds a second time
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = rh(__uint_as_float(acc[j]) * scale);
+    for (int j = 0; j < 32; ++j) v[j] = rh(sc(rh(__uint_as_float(acc[j]))));
     if (!row_valid) return;
     {
       __half* dst = static_cast<__half*>(pyr.ptr[0]) + row * pyr.pitch[0] + n0;
@@ -280,6 +294,7 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   } else {
     // ---------------------------------------------------------------------- epilogue
     const int quad = warp & 3;                    // TMEM lane quadrant this warp may read
+    const Scaler sc{dims.denom, dims.rcp, dims.rcp_exact};
     int buf = 0;
     uint32_t bphase = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
@@ -298,7 +313,7 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         uint32_t acc[32];
         ptx::tmem_ld_32x32(taddr + c * 32, acc);
         ptx::tmem_ld_wait();
-        ChunkStore<OT>::run(acc, pyr, row, nt * kBlockN + c * 32, dims.scale, row_valid);
+        ChunkStore<OT>::run(acc, pyr, row, nt * kBlockN + c * 32, sc, row_valid);
       }
       ptx::tc_fence_before_sync();
       ptx::mbar_arrive(ptx::smem_u32(&s_tempty[buf]));
@@ -408,13 +423,14 @@ int64_t smoe_corr_build_workspace_bytes(int B, int C, int H, int W1, int W2, int
 }
 
 int smoe_corr_build(const void* fmap1, const void* fmap2, int in_dtype, int B, int C, int H, int W1,
-                    int W2, const smoe_pyramid_t* pyr, float scale, void* workspace,
+                    int W2, const smoe_pyramid_t* pyr, float denom, void* workspace,
                     int64_t workspace_bytes, unsigned flags, smoe_stream_t stream) {
   using namespace smoe;
   if (int rc = validate_pyramid(pyr, "build")) return rc;
   SMOE_REQUIRE(dtype_ok(in_dtype), SMOE_ERR_INVALID_ARG, "build: unknown input dtype %d", in_dtype);
   SMOE_REQUIRE(B >= 0 && C >= 1 && H >= 0 && W1 >= 0 && W2 >= 0, SMOE_ERR_INVALID_ARG,
                "build: bad dims B=%d C=%d H=%d W1=%d W2=%d", B, C, H, W1, W2);
+  SMOE_REQUIRE(denom > 0.f && denom < 3.0e38f, SMOE_ERR_INVALID_ARG, "build: denom must be positive");
   SMOE_REQUIRE(pyr->B == B && pyr->H == H && pyr->W1 == W1 && pyr->width[0] == W2, SMOE_ERR_INVALID_ARG,
                "build: pyramid dims (%d,%d,%d,W2=%d) do not match the feature maps (%d,%d,%d,W2=%d)",
                pyr->B, pyr->H, pyr->W1, pyr->width[0], B, H, W1, W2);
@@ -482,7 +498,12 @@ int smoe_corr_build(const void* fmap1, const void* fmap2, int in_dtype, int B, i
   dims.W1 = W1; dims.W2 = W2; dims.C = C; dims.H = H; dims.BH = B * H;
   dims.MT = (W1 + kBlockM - 1) / kBlockM;
   dims.NT = (W2 + kBlockN - 1) / kBlockN;
-  dims.scale = scale;
+  dims.denom = denom;
+  dims.rcp = 1.0f / denom;
+  {
+    int e = 0;
+    dims.rcp_exact = (frexpf(denom, &e) == 0.5f) ? 1 : 0;   // power of two
+  }
   const PyrDev d = to_dev(pyr);
   if (in_dtype == SMOE_DTYPE_F32) return launch_build<float, float>(ta, tb, d, dims, st);
   if (pyr->dtype == SMOE_DTYPE_F16) return launch_build<__half, __half>(ta, tb, d, dims, st);
