@@ -143,6 +143,13 @@ int smoe_corr_lookup_bwd(const smoe_pyramid_t* grad_pyr, const float* coords,
  */
 int smoe_corr_fold_pyramid_grad(const smoe_pyramid_t* grad_pyr, smoe_stream_t stream);
 
+/*
+ * Debug aid (not part of the reference interface): when a device buffer of
+ * 148 * 3 * 16 int64 is set on the calling thread, the next smoe_corr_build launches record
+ * per-CTA clock64 stamps of the producer / MMA / epilogue roles into it.  NULL disables.
+ */
+void smoe_corr_debug_set_timeline(void* device_buffer);
+
 #ifdef __cplusplus
 }
 #endif

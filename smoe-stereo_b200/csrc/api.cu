@@ -1,5 +1,6 @@
 // api.cu -- ABI bookkeeping: version, thread-local error string, pyramid layout arithmetic.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -13,6 +14,14 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("SMOE_CORR_PDL");     // opt-in: measured slower on B200 for this path
+    return e && e[0] && e[0] != '0';
+  }();
+  return on;
 }
 
 int validate_pyramid(const smoe_pyramid_t* p, const char* who) {

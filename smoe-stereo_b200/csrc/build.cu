@@ -14,11 +14,15 @@
 //               MN-major layout tcgen05 expects (no transpose pass, TMA zero-fills W/C tails).
 //   warp 1      allocates TMEM (2 x 256 fp32 columns) and issues tcgen05.mma
 //               (kind::tf32 for fp32 inputs, kind::f16 for fp16 inputs), fp32 accumulate.
-//   warps 2-5   epilogue: tcgen05.ld 32 columns at a time, scale, build the three pooled levels
-//               in registers (pooling runs along N == along a thread's own TMEM row), store all
-//               levels.  Accumulators are double buffered so this overlaps the next item's MMAs.
+//   warps 2-5   epilogue: tcgen05.ld 32 columns at a time, divide, build the three pooled levels
+//               in registers (pooling runs along N == along a thread's own TMEM row), stage the
+//               four levels of a 128-byte-wide column chunk in swizzled shared memory and write
+//               them with TMA tensor stores (full-line writes; TMA clips the W1/W2 tails, so
+//               floor-halving of odd widths needs no masking).  Accumulators are double buffered
+//               so this overlaps the next item's loads and MMAs.
 #include <cuda.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -28,13 +32,19 @@ namespace smoe {
 // ------------------------------------------------------------------------------ tile constants
 constexpr int kBlockM = 128;          // UMMA M (TMEM lanes)
 constexpr int kBlockN = 256;          // max UMMA N / accumulator columns per buffer
-constexpr int kStages = 4;
+constexpr int kStages = 3;
 constexpr int kStageABytes = 16 * 1024;   // 128 rows x KT channels
 constexpr int kStageBBytes = 32 * 1024;   // 256 cols x KT channels
 constexpr int kStageBytes = kStageABytes + kStageBBytes;
 constexpr int kBuildThreads = 192;
 constexpr int kTmemCols = 512;
-constexpr size_t kBuildSmemBytes = (size_t)kStages * kStageBytes + 1024;   // + alignment slack
+// epilogue staging: per warp 2 buffers x (32 rows x (128+64+32+16) bytes) for levels 0..3
+// (buffer padded to 8 KiB so that every level-0 tile stays 1 KiB aligned: the swizzle is a
+// function of the shared-memory address)
+constexpr int kStgL0 = 0, kStgL1 = 4096, kStgL2 = 6144, kStgL3 = 7168, kStgBytes = 8192;
+constexpr int kStgPerWarp = 2 * kStgBytes;
+constexpr size_t kBuildSmemBytes =
+    (size_t)kStages * kStageBytes + 4 * kStgPerWarp + 1024;   // + alignment slack
 
 template <typename T> struct OperandCfg;
 template <> struct OperandCfg<float> {
@@ -67,122 +77,136 @@ struct BuildDims {
 struct Scaler {
   float denom, rcp;
   int exact;
-  __device__ __forceinline__ float operator()(float x) const {
-    return exact ? x * rcp : __fdiv_rn(x, denom);
+  // Whole-chunk form: ONE uniform branch, then 32 independent operations.  (A per-element
+  // `exact ? mul : div` compiles to 32 serialized division regions; with a single epilogue warp
+  // per scheduler that cost ~6 us per 128x240 tile, profiles/r01/README.md.)
+  __device__ __forceinline__ void apply(const uint32_t (&acc)[32], float (&v)[32]) const {
+    if (exact) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) * rcp;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __fdiv_rn(__uint_as_float(acc[j]), denom);
+    }
+  }
+  __device__ __forceinline__ void apply_rounded_half(const uint32_t (&acc)[32], float (&v)[32]) const {
+    if (exact) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        v[j] = __half2float(__float2half_rn(__half2float(__float2half_rn(__uint_as_float(acc[j]))) * rcp));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        v[j] = __half2float(__float2half_rn(
+            __fdiv_rn(__half2float(__float2half_rn(__uint_as_float(acc[j]))), denom)));
+    }
   }
 };
 
 // ------------------------------------------------------------------------------------ epilogue
-// One thread owns one output row (pixel) and 32 consecutive level-0 columns starting at n0
-// (a multiple of 32).  Produces 32/16/8/4 values of levels 0..3 and stores them as 16-byte
-// vectors; columns >= width[i] are dropped (floor-halving of odd widths).
-template <typename OT> struct ChunkStore;
+// Staging tile of level i for one warp: 32 rows x (128 >> i) bytes, dense, with the TMA swizzle of
+// that row width (128B / 64B / 32B / none) applied to the 16-byte chunk index so that the 32
+// lanes (one row each) write without bank conflicts.  tile bases are 1 KiB / 512 B / 256 B aligned.
+__device__ __forceinline__ uint32_t stg_addr(uint32_t tile, int level, int row, int byte_off) {
+  const uint32_t lin = (uint32_t)row * (128u >> level) + (uint32_t)byte_off;
+  const uint32_t mask = level == 0 ? 7u : (level == 1 ? 3u : (level == 2 ? 1u : 0u));
+  return tile + (lin ^ (((lin >> 7) & mask) << 4));
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+__device__ __forceinline__ void st_shared_v4u(uint32_t addr, uint32_t a, uint32_t b, uint32_t c,
+                                              uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d)
+               : "memory");
+}
+__device__ __forceinline__ void st_shared_v2u(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
 
-template <> struct ChunkStore<float> {
-  __device__ static void run(const uint32_t (&acc)[32], const PyrDev& pyr, long long row, int n0,
-                             const Scaler& sc, bool row_valid) {
+// One thread owns one output row and 32 consecutive level-0 columns (sub-chunk `sub` of the
+// 128-byte-wide staging chunk).  Produces 32/16/8/4 values of levels 0..3.
+template <typename OT> struct ChunkStage;
+
+template <> struct ChunkStage<float> {
+  static constexpr int kSubChunks = 1;     // 32 fp32 columns == 128 bytes
+  __device__ static void run(const uint32_t (&acc)[32], uint32_t stg, int row, int /*sub*/,
+                             const Scaler& sc, int num_levels) {
     float v[32];
+    sc.apply(acc, v);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = sc(__uint_as_float(acc[j]));
-    if (!row_valid) return;
-    {
-      float* dst = static_cast<float*>(pyr.ptr[0]) + row * pyr.pitch[0] + n0;
-      const int w = pyr.width[0];
-#pragma unroll
-      for (int g = 0; g < 8; ++g)
-        if (n0 + 4 * g < w)
-          *reinterpret_cast<float4*>(dst + 4 * g) =
-              make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
-    }
-    if (pyr.num_levels < 2) return;
+    for (int g = 0; g < 8; ++g)
+      st_shared_v4(stg_addr(stg + kStgL0, 0, row, 16 * g), v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+    if (num_levels < 2) return;
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = (v[2 * j] + v[2 * j + 1]) * 0.5f;
-    {
-      float* dst = static_cast<float*>(pyr.ptr[1]) + row * pyr.pitch[1] + (n0 >> 1);
-      const int w = pyr.width[1];
 #pragma unroll
-      for (int g = 0; g < 4; ++g)
-        if ((n0 >> 1) + 4 * g < w)
-          *reinterpret_cast<float4*>(dst + 4 * g) =
-              make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
-    }
-    if (pyr.num_levels < 3) return;
+    for (int g = 0; g < 4; ++g)
+      st_shared_v4(stg_addr(stg + kStgL1, 1, row, 16 * g), v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+    if (num_levels < 3) return;
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = (v[2 * j] + v[2 * j + 1]) * 0.5f;
-    {
-      float* dst = static_cast<float*>(pyr.ptr[2]) + row * pyr.pitch[2] + (n0 >> 2);
-      const int w = pyr.width[2];
 #pragma unroll
-      for (int g = 0; g < 2; ++g)
-        if ((n0 >> 2) + 4 * g < w)
-          *reinterpret_cast<float4*>(dst + 4 * g) =
-              make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
-    }
-    if (pyr.num_levels < 4) return;
+    for (int g = 0; g < 2; ++g)
+      st_shared_v4(stg_addr(stg + kStgL2, 2, row, 16 * g), v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+    if (num_levels < 4) return;
 #pragma unroll
     for (int j = 0; j < 4; ++j) v[j] = (v[2 * j] + v[2 * j + 1]) * 0.5f;
-    if ((n0 >> 3) < pyr.width[3])
-      *reinterpret_cast<float4*>(static_cast<float*>(pyr.ptr[3]) + row * pyr.pitch[3] + (n0 >> 3)) =
-          make_float4(v[0], v[1], v[2], v[3]);
+    st_shared_v4(stg_addr(stg + kStgL3, 3, row, 0), v[0], v[1], v[2], v[3]);
   }
 };
 
 // fp16 pyramid: every level is rounded to half and the next level is pooled from the ROUNDED
 // values with an fp32 sum, which is what F.avg_pool2d does on a half tensor (core/corr.py:42).
-template <> struct ChunkStore<__half> {
-  __device__ static void pack_store(__half* dst, const float* v, int n) {   // n = 8 or 4 halves
-    __half2 h[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-    if (n == 8)
-      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(h);
-    else
-      *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(h);
-  }
+// 64 fp16 columns == 128 bytes, processed as two 32-column sub-chunks.
+template <> struct ChunkStage<__half> {
+  static constexpr int kSubChunks = 2;
   __device__ static float rh(float x) { return __half2float(__float2half_rn(x)); }
-  __device__ static void run(const uint32_t (&acc)[32], const PyrDev& pyr, long long row, int n0,
-                             const Scaler& sc, bool row_valid) {
+  __device__ static void run(const uint32_t (&acc)[32], uint32_t stg, int row, int sub,
+                             const Scaler& sc, int num_levels) {
     float v[32];
     // the reference's einsum output is already fp16; the division then rounds a second time
+    sc.apply_rounded_half(acc, v);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = rh(sc(rh(__uint_as_float(acc[j]))));
-    if (!row_valid) return;
-    {
-      __half* dst = static_cast<__half*>(pyr.ptr[0]) + row * pyr.pitch[0] + n0;
-      const int w = pyr.width[0];
-#pragma unroll
-      for (int g = 0; g < 4; ++g)
-        if (n0 + 8 * g < w) pack_store(dst + 8 * g, v + 8 * g, 8);
-    }
-    if (pyr.num_levels < 2) return;
+    for (int g = 0; g < 4; ++g)
+      st_shared_v4u(stg_addr(stg + kStgL0, 0, row, 64 * sub + 16 * g), pack_h2(v[8 * g], v[8 * g + 1]),
+                    pack_h2(v[8 * g + 2], v[8 * g + 3]), pack_h2(v[8 * g + 4], v[8 * g + 5]),
+                    pack_h2(v[8 * g + 6], v[8 * g + 7]));
+    if (num_levels < 2) return;
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = rh((v[2 * j] + v[2 * j + 1]) * 0.5f);
-    {
-      __half* dst = static_cast<__half*>(pyr.ptr[1]) + row * pyr.pitch[1] + (n0 >> 1);
-      const int w = pyr.width[1];
 #pragma unroll
-      for (int g = 0; g < 2; ++g)
-        if ((n0 >> 1) + 8 * g < w) pack_store(dst + 8 * g, v + 8 * g, 8);
-    }
-    if (pyr.num_levels < 3) return;
+    for (int g = 0; g < 2; ++g)
+      st_shared_v4u(stg_addr(stg + kStgL1, 1, row, 32 * sub + 16 * g), pack_h2(v[8 * g], v[8 * g + 1]),
+                    pack_h2(v[8 * g + 2], v[8 * g + 3]), pack_h2(v[8 * g + 4], v[8 * g + 5]),
+                    pack_h2(v[8 * g + 6], v[8 * g + 7]));
+    if (num_levels < 3) return;
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = rh((v[2 * j] + v[2 * j + 1]) * 0.5f);
-    if ((n0 >> 2) < pyr.width[2])
-      pack_store(static_cast<__half*>(pyr.ptr[2]) + row * pyr.pitch[2] + (n0 >> 2), v, 8);
-    if (pyr.num_levels < 4) return;
+    st_shared_v4u(stg_addr(stg + kStgL2, 2, row, 16 * sub), pack_h2(v[0], v[1]), pack_h2(v[2], v[3]),
+                  pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+    if (num_levels < 4) return;
 #pragma unroll
     for (int j = 0; j < 4; ++j) v[j] = rh((v[2 * j] + v[2 * j + 1]) * 0.5f);
-    v[4] = v[5] = v[6] = v[7] = 0.f;
-    if ((n0 >> 3) < pyr.width[3])
-      pack_store(static_cast<__half*>(pyr.ptr[3]) + row * pyr.pitch[3] + (n0 >> 3), v, 4);
+    st_shared_v2u(stg_addr(stg + kStgL3, 3, row, 8 * sub), pack_h2(v[0], v[1]), pack_h2(v[2], v[3]));
   }
+};
+
+struct OutMaps {
+  CUtensorMap lvl[SMOE_MAX_LEVELS];   // 3-D (W2_i, W1, B*H) maps of the pyramid levels
 };
 
 // -------------------------------------------------------------------------------------- kernel
 template <typename IT, typename OT>
 __global__ void __launch_bounds__(kBuildThreads, 1)
 corr_build_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                  const PyrDev pyr, const BuildDims dims) {
+                  const __grid_constant__ OutMaps omaps, const int num_levels, const BuildDims dims,
+                  long long* __restrict__ timeline, const int dbg) {
   using Cfg = OperandCfg<IT>;
   constexpr int kSlabBytes = Cfg::kKT * 128;                 // one W slab x KT channels
   constexpr int kSlabsA = kBlockM / Cfg::kSlab;
@@ -195,6 +219,12 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   __shared__ __align__(8) uint64_t s_full[kStages], s_empty[kStages], s_tfull[2], s_tempty[2];
   __shared__ uint32_t s_tmem_base;
 
+  // debug timeline (smoe_corr_debug_set_timeline): clock64 stamps, 16 slots per role per CTA
+  const long long t_origin = clock64();
+  auto stamp = [&](int role, int slot) {
+    if (timeline != nullptr && slot < 16)
+      timeline[((long long)blockIdx.x * 3 + role) * 16 + slot] = clock64() - t_origin;
+  };
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;   // swizzle atoms: 1 KiB
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_items = dims.BH * dims.MT * dims.NT;
@@ -203,6 +233,7 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmap_a);
     ptx::prefetch_tensormap(&tmap_b);
+    for (int i = 0; i < num_levels; ++i) ptx::prefetch_tensormap(&omaps.lvl[i]);
     for (int i = 0; i < kStages; ++i) {
       ptx::mbar_init(ptx::smem_u32(&s_full[i]), 1);
       ptx::mbar_init(ptx::smem_u32(&s_empty[i]), 1);
@@ -221,13 +252,19 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = s_tmem_base;
+  // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) may overlap the
+  // tail of the previous kernel in the stream; global memory is touched only after the wait.
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      int it = 0;
+      stamp(0, 0);
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
         const int nt = item % dims.NT;
         const int mt = (item / dims.NT) % dims.MT;
         const int bh = item / (dims.NT * dims.MT);
@@ -250,6 +287,7 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                              ks * Cfg::kKT, b);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
+        stamp(0, 1 + it);                 // all loads of item `it` issued
       }
     }
   } else if (warp == 1) {
@@ -259,7 +297,8 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       uint32_t phase = 0;
       int buf = 0;
       uint32_t bphase = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      int it = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
         const int nt = item % dims.NT;
         const int n_valid = min(kBlockN, dims.W2 - nt * kBlockN);
         const uint32_t n_mma = (uint32_t)((n_valid + 15) & ~15);
@@ -270,6 +309,8 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         for (int ks = 0; ks < num_k; ++ks) {
           ptx::mbar_wait(ptx::smem_u32(&s_full[stage]), phase);
           ptx::tc_fence_after_sync();
+          if (ks == 0) stamp(1, 3 * it);            // first stage of the item landed
+          if (ks == num_k - 1) stamp(1, 3 * it + 1);  // last stage landed
           const uint32_t sa = smem_base + stage * kStageBytes;
           const uint32_t sb = sa + kStageABytes;
 #pragma unroll
@@ -287,39 +328,69 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
         ptx::tc_commit(ptx::smem_u32(&s_tfull[buf]));          // accumulator ready
+        stamp(1, 3 * it + 2);
         buf ^= 1;
         if (buf == 0) bphase ^= 1u;
       }
     }
   } else {
     // ---------------------------------------------------------------------- epilogue
+    constexpr int kSub = ChunkStage<OT>::kSubChunks;       // 32-column sub-chunks per 128-byte chunk
+    constexpr int kChunkCols = 32 * kSub;
     const int quad = warp & 3;                    // TMEM lane quadrant this warp may read
     const Scaler sc{dims.denom, dims.rcp, dims.rcp_exact};
+    const uint32_t stg_base = smem_base + kStages * kStageBytes + (uint32_t)(warp - 2) * kStgPerWarp;
     int buf = 0;
     uint32_t bphase = 0;
-    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+    int stg_sel = 0;
+    int it = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
       const int nt = item % dims.NT;
       const int mt = (item / dims.NT) % dims.MT;
       const int bh = item / (dims.NT * dims.MT);
       const int n_valid = min(kBlockN, dims.W2 - nt * kBlockN);
-      const int m = mt * kBlockM + quad * 32 + lane;
-      const bool row_valid = m < dims.W1;
-      const long long row = (long long)bh * dims.W1 + m;
+      const int m0 = mt * kBlockM + quad * 32;          // first output row of this warp
       ptx::mbar_wait(ptx::smem_u32(&s_tfull[buf]), bphase);
       ptx::tc_fence_after_sync();
+      if (warp == 2 && lane == 0) stamp(2, 2 * it);          // accumulator of the item complete
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)buf * kBlockN;
-      const int chunks = (n_valid + 31) >> 5;
+      const int chunks = (n_valid + kChunkCols - 1) / kChunkCols;
       for (int c = 0; c < chunks; ++c) {
-        uint32_t acc[32];
-        ptx::tmem_ld_32x32(taddr + c * 32, acc);
-        ptx::tmem_ld_wait();
-        ChunkStore<OT>::run(acc, pyr, row, nt * kBlockN + c * 32, sc, row_valid);
+        const uint32_t stg = stg_base + (uint32_t)stg_sel * kStgBytes;
+        // the TMA stores that last read this staging buffer (two chunks ago) must have drained
+        if (lane == 0) ptx::tma_store_wait_read<1>();
+        __syncwarp();
+#pragma unroll
+        for (int sub = 0; sub < kSub; ++sub) {
+          if (c * kChunkCols + sub * 32 < n_valid || sub == 0) {
+            uint32_t acc[32];
+            ptx::tmem_ld_32x32(taddr + c * kChunkCols + sub * 32, acc);
+            ptx::tmem_ld_wait();
+            if (!(dbg & 4)) ChunkStage<OT>::run(acc, stg, lane, sub, sc, num_levels);
+          }
+        }
+        ptx::fence_proxy_async_smem();             // generic-proxy smem writes -> async proxy (TMA)
+        __syncwarp();
+        if (lane == 0 && m0 < dims.W1 && !(dbg & 1)) {
+          const int n0 = nt * kBlockN + c * kChunkCols;
+          ptx::tma_store_3d(&omaps.lvl[0], stg + kStgL0, n0, m0, bh);
+          if (!(dbg & 2)) {
+          if (num_levels > 1) ptx::tma_store_3d(&omaps.lvl[1], stg + kStgL1, n0 >> 1, m0, bh);
+          if (num_levels > 2) ptx::tma_store_3d(&omaps.lvl[2], stg + kStgL2, n0 >> 2, m0, bh);
+          if (num_levels > 3) ptx::tma_store_3d(&omaps.lvl[3], stg + kStgL3, n0 >> 3, m0, bh);
+          }
+        }
+        if (lane == 0) ptx::tma_store_commit();
+        stg_sel ^= 1;
       }
       ptx::tc_fence_before_sync();
       ptx::mbar_arrive(ptx::smem_u32(&s_tempty[buf]));
+      if (warp == 2 && lane == 0) stamp(2, 2 * it + 1);      // epilogue of the item issued
       buf ^= 1;
       if (buf == 0) bphase ^= 1u;
     }
+    if (lane == 0) ptx::tma_store_wait_all<0>();   // global writes complete before the CTA exits
+    if (warp == 2 && lane == 0) stamp(2, 15);
   }
 
   ptx::tc_fence_before_sync();
@@ -336,6 +407,8 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 template <typename T>
 __global__ void __launch_bounds__(256)
 pad_rows_kernel(const T* __restrict__ src, T* __restrict__ dst, long long rows, int W, int Wp) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long total = rows * Wp;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -392,8 +465,34 @@ static int make_fmap_tmap(CUtensorMap* out, const void* base, int dtype, bool tf
   return SMOE_OK;
 }
 
+// 3-D map over one pyramid level: dims (W2_i, W1, B*H), box = (128 >> i bytes) x 32 rows x 1,
+// swizzle matched to the box row width (the staging tiles of ChunkStage).
+static int make_level_tmap(CUtensorMap* out, const smoe_pyramid_t* pyr, int level) {
+  EncodeTiledFn enc = encode_fn();
+  SMOE_REQUIRE(enc != nullptr, SMOE_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  const int es = dtype_size(pyr->dtype);
+  const cuuint64_t gdim[3] = {(cuuint64_t)pyr->width[level], (cuuint64_t)pyr->W1,
+                              (cuuint64_t)pyr->B * pyr->H};
+  const cuuint64_t gstr[2] = {(cuuint64_t)pyr->pitch[level] * es,
+                              (cuuint64_t)pyr->W1 * pyr->pitch[level] * es};
+  const cuuint32_t box[3] = {(cuuint32_t)((128 >> level) / es), 32u, 1u};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  static const CUtensorMapSwizzle kSw[4] = {CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_SWIZZLE_64B,
+                                            CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_SWIZZLE_NONE};
+  const CUresult r = enc(out, pyr->dtype == SMOE_DTYPE_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                                           : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                         3, pyr->level_ptr[level], gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         kSw[level], CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SMOE_REQUIRE(r == CUDA_SUCCESS, SMOE_ERR_CUDA,
+               "cuTensorMapEncodeTiled (pyramid level %d) failed with CUresult %d", level, (int)r);
+  return SMOE_OK;
+}
+
+static thread_local long long* g_timeline = nullptr;   // smoe_corr_debug_set_timeline
+static const int g_dbg = [] { const char* e = getenv("SMOE_CORR_DEBUG_FLAGS"); return e ? atoi(e) : 0; }();
+
 template <typename IT, typename OT>
-static int launch_build(const CUtensorMap& ta, const CUtensorMap& tb, const PyrDev& pyr,
+static int launch_build(const CUtensorMap& ta, const CUtensorMap& tb, const OutMaps& om, int num_levels,
                         const BuildDims& dims, cudaStream_t st) {
   auto kern = corr_build_kernel<IT, OT>;
   SMOE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -403,13 +502,18 @@ static int launch_build(const CUtensorMap& ta, const CUtensorMap& tb, const PyrD
   SMOE_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const long long items = (long long)dims.BH * dims.MT * dims.NT;
   const int grid = (int)(items < sms ? items : sms);
-  kern<<<grid, kBuildThreads, kBuildSmemBytes, st>>>(ta, tb, pyr, dims);
+  SMOE_CUDA_OK(launch_kernel(kern, dim3(grid), dim3(kBuildThreads), kBuildSmemBytes, st, ta, tb, om,
+                             num_levels, dims, g_timeline, g_dbg));
   return check_launch("corr_build_kernel");
 }
 
 }  // namespace smoe
 
 extern "C" {
+
+void smoe_corr_debug_set_timeline(void* device_buffer) {
+  smoe::g_timeline = static_cast<long long*>(device_buffer);
+}
 
 int64_t smoe_corr_build_workspace_bytes(int B, int C, int H, int W1, int W2, int in_dtype) {
   using namespace smoe;
@@ -449,8 +553,8 @@ int smoe_corr_build(const void* fmap1, const void* fmap2, int in_dtype, int B, i
     SMOE_REQUIRE(aligned16(pyr->level_ptr[i]) && (pyr->pitch[i] * oes) % 16 == 0 &&
                      ((int64_t)pyr->width[i] + per16 - 1) / per16 * per16 <= pyr->pitch[i],
                  SMOE_ERR_INVALID_ARG,
-                 "build: level %d must be 16-byte aligned with a 16-byte-multiple pitch that holds the "
-                 "width rounded up to 16 bytes (use smoe_corr_pyramid_layout)", i);
+                 "build: level %d must be 16-byte aligned with a 16-byte-multiple pitch (TMA store) "
+                 "(use smoe_corr_pyramid_layout)", i);
   }
   SMOE_REQUIRE((long long)B * H * ((W1 + kBlockM - 1) / kBlockM) * ((W2 + kBlockN - 1) / kBlockN) <
                    (1ll << 31),
@@ -476,11 +580,11 @@ int smoe_corr_build(const void* fmap1, const void* fmap2, int in_dtype, int B, i
       long long blocks = (total + 255) / 256;
       if (blocks > 148ll * 16) blocks = 148ll * 16;
       if (es == 4)
-        pad_rows_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(static_cast<const float*>(src),
-                                                               static_cast<float*>(dst), rows, W, Wp);
+        launch_kernel(pad_rows_kernel<float>, dim3((unsigned)blocks), dim3(256), 0, st,
+                      static_cast<const float*>(src), static_cast<float*>(dst), rows, W, Wp);
       else
-        pad_rows_kernel<__half><<<(unsigned)blocks, 256, 0, st>>>(
-            static_cast<const __half*>(src), static_cast<__half*>(dst), rows, W, Wp);
+        launch_kernel(pad_rows_kernel<__half>, dim3((unsigned)blocks), dim3(256), 0, st,
+                      static_cast<const __half*>(src), static_cast<__half*>(dst), rows, W, Wp);
       ws += (rows * Wp * es + 255) / 256 * 256;
       return dst;
     };
@@ -504,10 +608,15 @@ int smoe_corr_build(const void* fmap1, const void* fmap2, int in_dtype, int B, i
     int e = 0;
     dims.rcp_exact = (frexpf(denom, &e) == 0.5f) ? 1 : 0;   // power of two
   }
-  const PyrDev d = to_dev(pyr);
-  if (in_dtype == SMOE_DTYPE_F32) return launch_build<float, float>(ta, tb, d, dims, st);
-  if (pyr->dtype == SMOE_DTYPE_F16) return launch_build<__half, __half>(ta, tb, d, dims, st);
-  return launch_build<__half, float>(ta, tb, d, dims, st);
+  // levels whose width has shrunk to 0 have nothing to write
+  int levels = pyr->num_levels;
+  while (levels > 1 && pyr->width[levels - 1] == 0) --levels;
+  OutMaps om;
+  for (int i = 0; i < SMOE_MAX_LEVELS; ++i)
+    if (int rc = make_level_tmap(&om.lvl[i], pyr, i < levels ? i : 0)) return rc;
+  if (in_dtype == SMOE_DTYPE_F32) return launch_build<float, float>(ta, tb, om, levels, dims, st);
+  if (pyr->dtype == SMOE_DTYPE_F16) return launch_build<__half, __half>(ta, tb, om, levels, dims, st);
+  return launch_build<__half, float>(ta, tb, om, levels, dims, st);
 }
 
 }  // extern "C"

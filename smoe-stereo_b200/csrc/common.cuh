@@ -40,6 +40,33 @@ inline int check_launch(const char* what) {
   return SMOE_OK;
 }
 
+// Programmatic dependent launch (PDL): the kernel may become resident while its predecessor in
+// the stream is still draining; it must execute pdl_wait() before touching global memory.
+// Opt-in with SMOE_CORR_PDL=1: on B200 back-to-back lookups measured ~10% SLOWER with PDL
+// (profiles/r01/README.md), so plain stream-ordered launches are the default.
+bool pdl_enabled();   // api.cu
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                 cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 inline int dtype_size(int dtype) { return dtype == SMOE_DTYPE_F16 ? 2 : 4; }
 inline bool dtype_ok(int dtype) { return dtype == SMOE_DTYPE_F32 || dtype == SMOE_DTYPE_F16; }
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

@@ -13,6 +13,8 @@
 //  * backward, overwrite: one pass writes every element of the dense gradient (zeros outside the
 //    window), replacing the reference's zeros_like + scatter pair (sampler_kernel.cu:148-163).
 //  * generic scalar kernels cover unaligned widths / pitches and radii other than 4.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace smoe {
@@ -21,27 +23,47 @@ constexpr int kTilePx = 32;       // pixels per CTA tile (one 128-byte line of f
 constexpr int kFwdThreads = 128;  // 4 lanes per pixel
 
 // ----------------------------------------------------------------------------- forward (vector)
-template <typename VT, typename OT, int R, int NL>
-__global__ void __launch_bounds__(kFwdThreads)
+// Shared "window space" tile: for every (level, pixel) the 4*EPL interpolated values
+// e[i] = lerp(v[i], v[i+1]) of the aligned chunks covering the pixel's window, plus the shift s
+// (window start inside the first chunk).  Output channel k of that level is e[s + k]: the
+// data-dependent shift is applied on the READ side, so the write side is one 16-byte store per
+// chunk.  Row stride WIN+4 words and an XOR of the chunk index with (p>>3)&3 keep both the
+// 16-byte writes and the shifted scalar reads (lane = pixel) nearly bank-conflict free.
+template <int EPL> struct WinTile {
+  static constexpr int kWin = 4 * EPL;
+  static constexpr int kStride = kWin + 4;                 // words per (level,pixel) row
+  __device__ static __forceinline__ int chunk_word(int p, int chunk) {
+    return p * kStride + ((chunk ^ ((p >> 3) & 3)) << 2);
+  }
+  __device__ static __forceinline__ int elem_word(int p, int e) {
+    return chunk_word(p, e >> 2) + (e & 3);
+  }
+};
+
+template <typename VT, typename OT, int R, int NL, int TPX>
+__global__ void __launch_bounds__(4 * TPX)
 lookup_fwd_vec_kernel(PyrDev pyr, const float* __restrict__ coords, long long coords_bstride,
                       float coord_scale, OT* __restrict__ out, int HW) {
   constexpr int EPL = Vec16<VT>::N;          // elements per 16-byte chunk
   constexpr int LOG_EPL = (EPL == 4) ? 2 : 3;
   constexpr int RD = 2 * R + 1;
+  using Tile = WinTile<EPL>;
   static_assert(EPL - 1 + 2 * R + 2 <= 4 * EPL, "window must fit the 4 chunks of a lane group");
-  __shared__ OT s_out[NL * RD][kTilePx + 1];
+  __shared__ __align__(16) float s_win[NL][TPX * Tile::kStride];
+  __shared__ int s_shift[NL][TPX];
 
+  pdl_launch_dependents();   // successors may become resident; they block in their own pdl_wait
+  pdl_wait();                // coords / pyramid come from earlier kernels in the stream
   const int tid = threadIdx.x;
   const int p = tid >> 2, q = tid & 3;
   const int b = blockIdx.y;
-  const int hw0 = blockIdx.x * kTilePx;
+  const int hw0 = blockIdx.x * TPX;
   const int hw = hw0 + p;
   const bool valid = hw < HW;
   const float x0 = valid ? __ldg(coords + (long long)b * coords_bstride + hw) * coord_scale : 0.f;
   const long long row = (long long)b * HW + hw;
 
   float v[NL][EPL];
-  int sh[NL];
   float dxs[NL];
   float lscale = 1.0f;
 #pragma unroll
@@ -51,7 +73,7 @@ lookup_fwd_vec_kernel(PyrDev pyr, const float* __restrict__ coords, long long co
     lscale *= 0.5f;
     const int s = base & (EPL - 1);
     const int ci = (base >> LOG_EPL) + q;          // arithmetic shift == floor division
-    sh[l] = s;
+    if (q == 0) s_shift[l][p] = s;
     const int width = pyr.width[l];
     const int nchunks = (width + EPL - 1) >> LOG_EPL;
     const bool need = valid && (q * EPL < s + 2 * R + 2) && ci >= 0 && ci < nchunks;
@@ -71,20 +93,31 @@ lookup_fwd_vec_kernel(PyrDev pyr, const float* __restrict__ coords, long long co
   for (int l = 0; l < NL; ++l) {
     const float nxt = __shfl_down_sync(0xffffffffu, v[l][0], 1);   // first element of chunk q+1
     const float dx = dxs[l];
+    float e[EPL];
 #pragma unroll
-    for (int j = 0; j < EPL; ++j) {
-      const float v1 = (j + 1 < EPL) ? v[l][j + 1] : nxt;
-      const OT e = lerp_ref<OT>(v[l][j], v1, dx);
-      const int k = q * EPL + j - sh[l];
-      if (k >= 0 && k < RD) s_out[l * RD + k][p] = e;
-    }
+    for (int j = 0; j < EPL; ++j)
+      e[j] = to_float(lerp_ref<OT>(v[l][j], (j + 1 < EPL) ? v[l][j + 1] : nxt, dx));
+#pragma unroll
+    for (int h = 0; h < EPL / 4; ++h)
+      *reinterpret_cast<float4*>(&s_win[l][Tile::chunk_word(p, q * (EPL / 4) + h)]) =
+          make_float4(e[4 * h], e[4 * h + 1], e[4 * h + 2], e[4 * h + 3]);
   }
   __syncthreads();
+  // output phase: lane = pixel; a warp takes one (level, 32-pixel group) at a time, so every
+  // store instruction writes one full 128-byte line of one output channel
   const int warp = tid >> 5, lane = tid & 31;
-  if (hw0 + lane < HW) {
-    OT* dst = out + (long long)b * (NL * RD) * HW + hw0 + lane;
-#pragma unroll 4
-    for (int c = warp; c < NL * RD; c += kFwdThreads / 32) dst[(long long)c * HW] = s_out[c][lane];
+  constexpr int kGroups = TPX / 32, kWarps = TPX / 8;
+  for (int item = warp; item < NL * kGroups; item += kWarps) {
+    const int l = item % NL, pg = item / NL;
+    const int pp = pg * 32 + lane;
+    if (hw0 + pp < HW) {
+      OT* dst = out + ((long long)b * (NL * RD) + l * RD) * HW + hw0 + pp;
+      const int sft = s_shift[l][pp];
+      const float* wrow = s_win[l];
+#pragma unroll
+      for (int k = 0; k < RD; ++k)
+        dst[(long long)k * HW] = from_float<OT>(wrow[Tile::elem_word(pp, sft + k)]);
+    }
   }
 }
 
@@ -93,6 +126,8 @@ template <typename VT, typename OT>
 __global__ void __launch_bounds__(128)
 lookup_fwd_generic_kernel(PyrDev pyr, const float* __restrict__ coords, long long coords_bstride,
                           float coord_scale, int R, OT* __restrict__ out, int HW) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int hw = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
   if (hw >= HW) return;
@@ -149,6 +184,8 @@ lookup_bwd_acc_vec_kernel(PyrDev gp, const float* __restrict__ coords, long long
   constexpr int RD = 2 * R + 1;
   __shared__ float s_g[NL * RD][kTilePx + 1];
 
+  pdl_launch_dependents();
+  pdl_wait();
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.y;
@@ -201,6 +238,8 @@ template <typename GT>
 __global__ void __launch_bounds__(128)
 lookup_bwd_acc_generic_kernel(PyrDev gp, const float* __restrict__ coords, long long coords_bstride,
                               float coord_scale, int R, const GT* __restrict__ gout, int HW) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int hw = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
   if (hw >= HW) return;
@@ -239,6 +278,8 @@ lookup_bwd_dense_kernel(PyrDev gp, const float* __restrict__ coords, long long c
   const int RD = 2 * R + 1;
   const int NC = gp.num_levels * RD;
   float* s_x = s_dyn + NC * (kTilePx + 1);
+  pdl_launch_dependents();
+  pdl_wait();
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.y;
@@ -293,6 +334,8 @@ lookup_bwd_dense_kernel(PyrDev gp, const float* __restrict__ coords, long long c
 // falls outside its width (the column an odd level dropped, core/corr.py:124).
 __global__ void __launch_bounds__(256)
 fold_grad_kernel(PyrDev gp, long long rows) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int w0 = gp.width[0];
   const long long total = rows * w0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -328,12 +371,33 @@ static bool vec_ok(const smoe_pyramid_t* p) {
   return true;
 }
 
+// Pixels per CTA (32 / 64 / 128; 4 lanes per pixel).  SMOE_CORR_LOOKUP_TILE overrides for experiments.
+static int pick_fwd_tile(long long px) {
+  static const int forced = [] { const char* e = getenv("SMOE_CORR_LOOKUP_TILE"); return e ? atoi(e) : 0; }();
+  if (forced == 32 || forced == 64 || forced == 128) return forced;
+  (void)px;
+  return 32;   // measured best at every size tried (cfg1: 3.65/3.80/4.04 us, cfg3: 32.8/33.7/35.5 us)
+}
+
 template <typename VT, typename OT, int NL>
 static void launch_fwd_vec(const PyrDev& d, const float* coords, long long cbs, float cs, void* out,
                            int HW, int B, cudaStream_t st) {
-  dim3 grid((HW + kTilePx - 1) / kTilePx, B);
-  lookup_fwd_vec_kernel<VT, OT, 4, NL><<<grid, kFwdThreads, 0, st>>>(d, coords, cbs, cs,
-                                                                    static_cast<OT*>(out), HW);
+  int tile = pick_fwd_tile((long long)HW * B);
+  if (sizeof(VT) == 2 && tile == 128) tile = 64;   // fp16 window tile: 128 px would exceed 48 KB smem
+  dim3 grid((HW + tile - 1) / tile, B);
+  if constexpr (sizeof(VT) == 4) {
+    if (tile == 128) {
+      launch_kernel(lookup_fwd_vec_kernel<VT, OT, 4, NL, 128>, grid, dim3(512), 0, st, d, coords, cbs,
+                    cs, static_cast<OT*>(out), HW);
+      return;
+    }
+  }
+  if (tile == 64)
+    launch_kernel(lookup_fwd_vec_kernel<VT, OT, 4, NL, 64>, grid, dim3(256), 0, st, d, coords, cbs, cs,
+                  static_cast<OT*>(out), HW);
+  else
+    launch_kernel(lookup_fwd_vec_kernel<VT, OT, 4, NL, 32>, grid, dim3(128), 0, st, d, coords, cbs, cs,
+                  static_cast<OT*>(out), HW);
 }
 
 template <typename VT, typename OT>
@@ -351,8 +415,8 @@ template <typename GT, int NL>
 static void launch_bwd_acc_vec(const PyrDev& d, const float* coords, long long cbs, float cs,
                                const void* gout, int HW, int B, cudaStream_t st) {
   dim3 grid((HW + kTilePx - 1) / kTilePx, B);
-  lookup_bwd_acc_vec_kernel<GT, 4, NL><<<grid, kFwdThreads, 0, st>>>(
-      d, coords, cbs, cs, static_cast<const GT*>(gout), HW);
+  launch_kernel(lookup_bwd_acc_vec_kernel<GT, 4, NL>, grid, dim3(kFwdThreads), 0, st, d, coords, cbs, cs,
+                static_cast<const GT*>(gout), HW);
 }
 
 template <typename GT>
@@ -377,11 +441,11 @@ static int launch_bwd_dense(const smoe_pyramid_t* gp, const PyrDev& d, const flo
   bool vec = vec_ok(gp);
   for (int i = 0; i < gp->num_levels; ++i) vec = vec && (gp->width[i] % VEC == 0);
   if (vec)
-    lookup_bwd_dense_kernel<VT, GT, VEC><<<grid, kDenseThreads, smem, st>>>(
-        d, coords, cbs, cs, R, static_cast<const GT*>(gout), HW);
+    launch_kernel(lookup_bwd_dense_kernel<VT, GT, VEC>, grid, dim3(kDenseThreads), smem, st, d, coords,
+                  cbs, cs, R, static_cast<const GT*>(gout), HW);
   else
-    lookup_bwd_dense_kernel<VT, GT, 1><<<grid, kDenseThreads, smem, st>>>(
-        d, coords, cbs, cs, R, static_cast<const GT*>(gout), HW);
+    launch_kernel(lookup_bwd_dense_kernel<VT, GT, 1>, grid, dim3(kDenseThreads), smem, st, d, coords,
+                  cbs, cs, R, static_cast<const GT*>(gout), HW);
   return SMOE_OK;
 }
 
@@ -421,14 +485,14 @@ int smoe_corr_lookup(const smoe_pyramid_t* pyr, const float* coords, int64_t coo
   } else {
     dim3 grid((unsigned)((HW + 127) / 128), pyr->B);
     if (!f16v)
-      lookup_fwd_generic_kernel<float, float><<<grid, 128, 0, st>>>(
-          d, coords, coords_batch_stride, coord_scale, radius, static_cast<float*>(out), (int)HW);
+      launch_kernel(lookup_fwd_generic_kernel<float, float>, grid, dim3(128), 0, st, d, coords,
+                    (long long)coords_batch_stride, coord_scale, radius, static_cast<float*>(out), (int)HW);
     else if (f16o)
-      lookup_fwd_generic_kernel<__half, __half><<<grid, 128, 0, st>>>(
-          d, coords, coords_batch_stride, coord_scale, radius, static_cast<__half*>(out), (int)HW);
+      launch_kernel(lookup_fwd_generic_kernel<__half, __half>, grid, dim3(128), 0, st, d, coords,
+                    (long long)coords_batch_stride, coord_scale, radius, static_cast<__half*>(out), (int)HW);
     else
-      lookup_fwd_generic_kernel<__half, float><<<grid, 128, 0, st>>>(
-          d, coords, coords_batch_stride, coord_scale, radius, static_cast<float*>(out), (int)HW);
+      launch_kernel(lookup_fwd_generic_kernel<__half, float>, grid, dim3(128), 0, st, d, coords,
+                    (long long)coords_batch_stride, coord_scale, radius, static_cast<float*>(out), (int)HW);
   }
   return check_launch("lookup forward");
 }
@@ -466,13 +530,13 @@ int smoe_corr_lookup_bwd(const smoe_pyramid_t* gp, const float* coords, int64_t 
     } else {
       dim3 grid((unsigned)((HW + 127) / 128), gp->B);
       if (f16g)
-        lookup_bwd_acc_generic_kernel<__half><<<grid, 128, 0, st>>>(
-            d, coords, coords_batch_stride, coord_scale, radius,
-            static_cast<const __half*>(grad_out), (int)HW);
+        launch_kernel(lookup_bwd_acc_generic_kernel<__half>, grid, dim3(128), 0, st, d, coords,
+                      (long long)coords_batch_stride, coord_scale, radius,
+                      static_cast<const __half*>(grad_out), (int)HW);
       else
-        lookup_bwd_acc_generic_kernel<float><<<grid, 128, 0, st>>>(
-            d, coords, coords_batch_stride, coord_scale, radius,
-            static_cast<const float*>(grad_out), (int)HW);
+        launch_kernel(lookup_bwd_acc_generic_kernel<float>, grid, dim3(128), 0, st, d, coords,
+                      (long long)coords_batch_stride, coord_scale, radius,
+                      static_cast<const float*>(grad_out), (int)HW);
     }
   } else {
     int rc;
@@ -503,7 +567,8 @@ int smoe_corr_fold_pyramid_grad(const smoe_pyramid_t* gp, smoe_stream_t stream) 
   const long long total = rows * gp->width[0];
   long long blocks = (total + 255) / 256;
   if (blocks > 148ll * 32) blocks = 148ll * 32;
-  fold_grad_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(to_dev(gp), rows);
+  launch_kernel(fold_grad_kernel, dim3((unsigned)blocks), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                to_dev(gp), rows);
   return check_launch("fold_pyramid_grad");
 }
 
