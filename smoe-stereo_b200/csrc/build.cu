@@ -32,7 +32,7 @@ namespace smoe {
 // ------------------------------------------------------------------------------ tile constants
 constexpr int kBlockM = 128;          // UMMA M (TMEM lanes)
 constexpr int kBlockN = 256;          // max UMMA N / accumulator columns per buffer
-constexpr int kStages = 3;
+constexpr int kStages = 4;
 constexpr int kStageABytes = 16 * 1024;   // 128 rows x KT channels
 constexpr int kStageBBytes = 32 * 1024;   // 256 cols x KT channels
 constexpr int kStageBytes = kStageABytes + kStageBBytes;
@@ -42,7 +42,8 @@ constexpr int kTmemCols = 512;
 // (buffer padded to 8 KiB so that every level-0 tile stays 1 KiB aligned: the swizzle is a
 // function of the shared-memory address)
 constexpr int kStgL0 = 0, kStgL1 = 4096, kStgL2 = 6144, kStgL3 = 7168, kStgBytes = 8192;
-constexpr int kStgPerWarp = 2 * kStgBytes;
+constexpr int kStgBufs = 1;                        // staging buffers per epilogue warp
+constexpr int kStgPerWarp = kStgBufs * kStgBytes;
 constexpr size_t kBuildSmemBytes =
     (size_t)kStages * kStageBytes + 4 * kStgPerWarp + 1024;   // + alignment slack
 
@@ -67,6 +68,7 @@ template <> struct OperandCfg<__half> {
 struct BuildDims {
   int W1, W2, C, H, BH;      // BH = B*H image rows
   int MT, NT;                // tiles per image row
+  int BN;                    // columns per N tile: W2 split evenly, rounded up to 32, <= kBlockN
   float denom;               // level0 = sum / denom   (core/corr.py:156: corr / sqrt(D))
   float rcp;                 // 1/denom, used when it is exact (denom a power of two)
   int rcp_exact;
@@ -269,7 +271,7 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const int mt = (item / dims.NT) % dims.MT;
         const int bh = item / (dims.NT * dims.MT);
         const int b = bh / dims.H, h = bh - b * dims.H;
-        const int n_valid = min(kBlockN, dims.W2 - nt * kBlockN);
+        const int n_valid = min(dims.BN, dims.W2 - nt * dims.BN);
         const int slabs_b = (n_valid + Cfg::kSlab - 1) / Cfg::kSlab;
         const uint32_t tx_bytes = (uint32_t)(kSlabsA + slabs_b) * kSlabBytes;
         for (int ks = 0; ks < num_k; ++ks) {
@@ -283,7 +285,7 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             ptx::tma_load_4d(sa + j * kSlabBytes, &tmap_a, full, mt * kBlockM + j * Cfg::kSlab, h,
                              ks * Cfg::kKT, b);
           for (int j = 0; j < slabs_b; ++j)
-            ptx::tma_load_4d(sb + j * kSlabBytes, &tmap_b, full, nt * kBlockN + j * Cfg::kSlab, h,
+            ptx::tma_load_4d(sb + j * kSlabBytes, &tmap_b, full, nt * dims.BN + j * Cfg::kSlab, h,
                              ks * Cfg::kKT, b);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
@@ -300,7 +302,7 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       int it = 0;
       for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
         const int nt = item % dims.NT;
-        const int n_valid = min(kBlockN, dims.W2 - nt * kBlockN);
+        const int n_valid = min(dims.BN, dims.W2 - nt * dims.BN);
         const uint32_t n_mma = (uint32_t)((n_valid + 15) & ~15);
         const uint32_t idesc = ptx::make_idesc_mn_major(Cfg::kFmt, kBlockM, n_mma);
         ptx::mbar_wait(ptx::smem_u32(&s_tempty[buf]), bphase ^ 1u);
@@ -348,7 +350,7 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const int nt = item % dims.NT;
       const int mt = (item / dims.NT) % dims.MT;
       const int bh = item / (dims.NT * dims.MT);
-      const int n_valid = min(kBlockN, dims.W2 - nt * kBlockN);
+      const int n_valid = min(dims.BN, dims.W2 - nt * dims.BN);
       const int m0 = mt * kBlockM + quad * 32;          // first output row of this warp
       ptx::mbar_wait(ptx::smem_u32(&s_tfull[buf]), bphase);
       ptx::tc_fence_after_sync();
@@ -358,7 +360,7 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       for (int c = 0; c < chunks; ++c) {
         const uint32_t stg = stg_base + (uint32_t)stg_sel * kStgBytes;
         // the TMA stores that last read this staging buffer (two chunks ago) must have drained
-        if (lane == 0) ptx::tma_store_wait_read<1>();
+        if (lane == 0) ptx::tma_store_wait_read<kStgBufs - 1>();
         __syncwarp();
 #pragma unroll
         for (int sub = 0; sub < kSub; ++sub) {
@@ -372,7 +374,7 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         ptx::fence_proxy_async_smem();             // generic-proxy smem writes -> async proxy (TMA)
         __syncwarp();
         if (lane == 0 && m0 < dims.W1 && !(dbg & 1)) {
-          const int n0 = nt * kBlockN + c * kChunkCols;
+          const int n0 = nt * dims.BN + c * kChunkCols;
           ptx::tma_store_3d(&omaps.lvl[0], stg + kStgL0, n0, m0, bh);
           if (!(dbg & 2)) {
           if (num_levels > 1) ptx::tma_store_3d(&omaps.lvl[1], stg + kStgL1, n0 >> 1, m0, bh);
@@ -381,7 +383,7 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           }
         }
         if (lane == 0) ptx::tma_store_commit();
-        stg_sel ^= 1;
+        stg_sel = (stg_sel + 1) % kStgBufs;
       }
       ptx::tc_fence_before_sync();
       ptx::mbar_arrive(ptx::smem_u32(&s_tempty[buf]));
@@ -602,6 +604,11 @@ int smoe_corr_build(const void* fmap1, const void* fmap2, int in_dtype, int B, i
   dims.W1 = W1; dims.W2 = W2; dims.C = C; dims.H = H; dims.BH = B * H;
   dims.MT = (W1 + kBlockM - 1) / kBlockM;
   dims.NT = (W2 + kBlockN - 1) / kBlockN;
+  {
+    const int cc = 128 / oes;   // columns per 128-byte epilogue chunk: 32 (fp32 out) / 64 (fp16 out)
+    dims.BN = ((W2 + dims.NT - 1) / dims.NT + cc - 1) / cc * cc;
+    if (dims.BN > kBlockN) dims.BN = kBlockN;
+  }
   dims.denom = denom;
   dims.rcp = 1.0f / denom;
   {

@@ -29,3 +29,9 @@ for name, role, slots in (("producer: start, item0 issued, item1 issued", 0, [0,
     a = t[:, role, slots]
     print(name)
     print("  median", np.median(a, axis=0), "\n  max   ", a.max(axis=0), "\n  cta0  ", a[0], "\n  cta147", a[147])
+if os.environ.get("TL_RAW"):
+    for cta in (0, 73, 147):
+        print("cta", cta)
+        print("  producer", t[cta, 0])
+        print("  mma     ", t[cta, 1])
+        print("  epilogue", t[cta, 2])
