@@ -139,6 +139,7 @@ def cpu_path_timer(wl, budget_s, min_runs=2):
     """Time the oracle's C port of the reference's CPU path (build + iters lookups)."""
     from oracle import corr_oracle as o
     o.build()
+    o.use_all_host_threads()
     f1, f2, coords = synth_inputs(wl, seed=0)
     base = o.CorrPathBaseline(wl["B"], wl["C"], wl["H"], wl["W"], wl["W"], wl["L"], wl["r"], wl["iters"])
     base.run(f1, f2, coords)            # warm-up (page faults, thread pool)
@@ -158,6 +159,7 @@ def run_reference_arm(args, wl, rank, world):
         return
     from oracle import corr_oracle as o
     o.build()
+    o.use_all_host_threads()            # torchrun exports OMP_NUM_THREADS=1; the baseline gets every core
     f1, f2, coords = synth_inputs(wl, seed=0)
     base = o.CorrPathBaseline(wl["B"], wl["C"], wl["H"], wl["W"], wl["W"], wl["L"], wl["r"], wl["iters"])
     for _ in range(max(args.warmup, 1)):
@@ -213,6 +215,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout = the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     sampler = ClockSampler(local_rank) if rank == 0 else None
 

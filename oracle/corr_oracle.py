@@ -249,3 +249,14 @@ class CorrPathBaseline:
 
 def num_threads() -> int:
     return int(lib().oracle_num_threads())
+
+
+def use_all_host_threads() -> int:
+    """Give the OpenMP port every host core this process may run on (launchers such as torchrun
+    export OMP_NUM_THREADS=1)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    lib().oracle_set_num_threads(n)
+    return num_threads()
