@@ -92,19 +92,38 @@ inline PyrDev to_dev(const smoe_pyramid_t* p) {
   return d;
 }
 
-// 16-byte vector of volume elements -> floats
+// 16-byte vector of volume elements -> floats.
+// The windows are 40-byte pieces scattered over 2-KB pixel rows.  With a plain ld.global /
+// ld.global.nc / .cg the L2 fills the whole 128-byte line from DRAM on a miss (measured 3.96
+// sectors per request, 144 MB of DRAM reads per cfg3 launch); the explicit L2::64B prefetch size
+// halves the fill (2.39 sectors per request, 87 MB) and L1::no_allocate keeps these
+// single-use lines out of L1 (profiles/r01/README.md, "load variants").
+__device__ __forceinline__ uint4 ld_window16(const void* p) {
+  uint4 t;
+  asm volatile("ld.global.L1::no_allocate.L2::64B.v4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w)
+               : "l"(p));
+  return t;
+}
+// STREAM=true : volume larger than L2 -> 64-byte fills, no L1 allocation (less DRAM traffic).
+// STREAM=false: L2-resident volume    -> read-only path; measured faster there (3.65 vs 4.50 us
+//               per cfg1 lookup) because nothing goes to DRAM anyway.
 template <typename T> struct Vec16;
 template <> struct Vec16<float> {
   static constexpr int N = 4;
+  template <bool STREAM>
   __device__ static void load(const float* p, float (&v)[4]) {
-    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    const uint4 u = STREAM ? ld_window16(p) : __ldg(reinterpret_cast<const uint4*>(p));
+    const float4 t = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z),
+                                 __uint_as_float(u.w));
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
   }
 };
 template <> struct Vec16<__half> {
   static constexpr int N = 8;
+  template <bool STREAM>
   __device__ static void load(const __half* p, float (&v)[8]) {
-    const uint4 t = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint4 t = STREAM ? ld_window16(p) : __ldg(reinterpret_cast<const uint4*>(p));
     const __half2* h = reinterpret_cast<const __half2*>(&t);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {

@@ -40,7 +40,7 @@ template <int EPL> struct WinTile {
   }
 };
 
-template <typename VT, typename OT, int R, int NL, int TPX>
+template <typename VT, typename OT, int R, int NL, int TPX, bool STREAM>
 __global__ void __launch_bounds__(4 * TPX)
 lookup_fwd_vec_kernel(PyrDev pyr, const float* __restrict__ coords, long long coords_bstride,
                       float coord_scale, OT* __restrict__ out, int HW) {
@@ -81,7 +81,7 @@ lookup_fwd_vec_kernel(PyrDev pyr, const float* __restrict__ coords, long long co
     for (int j = 0; j < EPL; ++j) v[l][j] = 0.f;
     if (need) {
       const VT* src = static_cast<const VT*>(pyr.ptr[l]) + row * pyr.pitch[l] + (long long)ci * EPL;
-      Vec16<VT>::load(src, v[l]);
+      Vec16<VT>::template load<STREAM>(src, v[l]);
       if ((ci + 1) * EPL > width) {                // tail chunk: mask elements >= width
 #pragma unroll
         for (int j = 0; j < EPL; ++j)
@@ -143,10 +143,10 @@ lookup_fwd_generic_kernel(PyrDev pyr, const float* __restrict__ coords, long lon
     const int width = pyr.width[l];
     const VT* src = static_cast<const VT*>(pyr.ptr[l]) + row * pyr.pitch[l];
     OT* dst = out + ((long long)b * pyr.num_levels * RD + (long long)l * RD) * HW + hw;
-    float prev = (base >= 0 && base < width) ? to_float(src[base]) : 0.f;
+    float prev = (base >= 0 && base < width) ? to_float(__ldcg(src + base)) : 0.f;
     for (int k = 0; k < RD; ++k) {
       const int i1 = base + k + 1;
-      const float nxt = (i1 >= 0 && i1 < width) ? to_float(src[i1]) : 0.f;
+      const float nxt = (i1 >= 0 && i1 < width) ? to_float(__ldcg(src + i1)) : 0.f;
       dst[(long long)k * HW] = lerp_ref<OT>(prev, nxt, dx);
       prev = nxt;
     }
@@ -218,7 +218,9 @@ lookup_bwd_acc_vec_kernel(PyrDev gp, const float* __restrict__ coords, long long
     if (!((q * EPL < s + 2 * R + 2) && ci >= 0 && ci < nchunks)) continue;
     float4* dst = reinterpret_cast<float4*>(static_cast<float*>(gp.ptr[l]) + row * gp.pitch[l] +
                                             (long long)ci * EPL);
-    float4 cur = *dst;
+    const uint4 cu = ld_window16(dst);      // 64-byte fills, not whole lines (see Vec16)
+    float4 cur = make_float4(__uint_as_float(cu.x), __uint_as_float(cu.y), __uint_as_float(cu.z),
+                             __uint_as_float(cu.w));
     float* c4 = reinterpret_cast<float*>(&cur);
 #pragma unroll
     for (int j = 0; j < EPL; ++j) {
@@ -229,7 +231,7 @@ lookup_bwd_acc_vec_kernel(PyrDev gp, const float* __restrict__ coords, long long
         c4[j] += BwdTap<float>::eval(gm1, g0, t > 0, t < RD, dx);
       }
     }
-    *dst = cur;
+    __stcg(dst, cur);
   }
 }
 
@@ -371,33 +373,36 @@ static bool vec_ok(const smoe_pyramid_t* p) {
   return true;
 }
 
-// Pixels per CTA (32 / 64 / 128; 4 lanes per pixel).  SMOE_CORR_LOOKUP_TILE overrides for experiments.
+// Pixels per CTA (32 / 64; 4 lanes per pixel).  SMOE_CORR_LOOKUP_TILE overrides for experiments.
 static int pick_fwd_tile(long long px) {
   static const int forced = [] { const char* e = getenv("SMOE_CORR_LOOKUP_TILE"); return e ? atoi(e) : 0; }();
-  if (forced == 32 || forced == 64 || forced == 128) return forced;
+  if (forced == 32 || forced == 64) return forced;
   (void)px;
   return 32;   // measured best at every size tried (cfg1: 3.65/3.80/4.04 us, cfg3: 32.8/33.7/35.5 us)
+}
+
+// A pyramid that cannot stay L2-resident (126 MB L2, minus the lookup's own outputs) is read with
+// the streaming load variant (Vec16).
+static bool volume_exceeds_l2(const PyrDev& d, long long rows, int elem_bytes) {
+  return rows * d.pitch[0] * elem_bytes > (96ll << 20);
 }
 
 template <typename VT, typename OT, int NL>
 static void launch_fwd_vec(const PyrDev& d, const float* coords, long long cbs, float cs, void* out,
                            int HW, int B, cudaStream_t st) {
   int tile = pick_fwd_tile((long long)HW * B);
-  if (sizeof(VT) == 2 && tile == 128) tile = 64;   // fp16 window tile: 128 px would exceed 48 KB smem
+  if (tile != 64) tile = 32;
   dim3 grid((HW + tile - 1) / tile, B);
-  if constexpr (sizeof(VT) == 4) {
-    if (tile == 128) {
-      launch_kernel(lookup_fwd_vec_kernel<VT, OT, 4, NL, 128>, grid, dim3(512), 0, st, d, coords, cbs,
-                    cs, static_cast<OT*>(out), HW);
-      return;
-    }
+  const bool big = volume_exceeds_l2(d, (long long)HW * B, (int)sizeof(VT));
+#define SMOE_LAUNCH_FWD(TPX, STREAM)                                                               \
+  launch_kernel(lookup_fwd_vec_kernel<VT, OT, 4, NL, TPX, STREAM>, grid, dim3(4 * TPX), 0, st, d,  \
+                coords, cbs, cs, static_cast<OT*>(out), HW)
+  if (tile == 64) {
+    if (big) SMOE_LAUNCH_FWD(64, true); else SMOE_LAUNCH_FWD(64, false);
+  } else {
+    if (big) SMOE_LAUNCH_FWD(32, true); else SMOE_LAUNCH_FWD(32, false);
   }
-  if (tile == 64)
-    launch_kernel(lookup_fwd_vec_kernel<VT, OT, 4, NL, 64>, grid, dim3(256), 0, st, d, coords, cbs, cs,
-                  static_cast<OT*>(out), HW);
-  else
-    launch_kernel(lookup_fwd_vec_kernel<VT, OT, 4, NL, 32>, grid, dim3(128), 0, st, d, coords, cbs, cs,
-                  static_cast<OT*>(out), HW);
+#undef SMOE_LAUNCH_FWD
 }
 
 template <typename VT, typename OT>
