@@ -18,6 +18,7 @@
  *   smoe_corr_lookup_bwd       sampler/sampler.cpp:34-45, sampler/sampler_kernel.cu:63-105,138-166
  *                              (corr_sampler.backward)
  *   smoe_corr_fold_pyramid_grad  autograd of core/corr.py:122-125 (avg_pool2d backward chain)
+ *   smoe_corr_build_bwd        autograd of core/corr.py:154-156 (einsum backward: d fmap1, d fmap2)
  *
  * Data layout
  * -----------
@@ -142,6 +143,18 @@ int smoe_corr_lookup_bwd(const smoe_pyramid_t* grad_pyr, const float* coords,
  *   g_{i-1}[., 2j] += g_i[., j]/2 ; g_{i-1}[., 2j+1] += g_i[., j]/2, for i = L-1 .. 1.
  */
 int smoe_corr_fold_pyramid_grad(const smoe_pyramid_t* grad_pyr, smoe_stream_t stream);
+
+/*
+ * Volume-build backward on tcgen05 tensor cores (kind::tf32): with G = grad_pyr level 0 after
+ * smoe_corr_fold_pyramid_grad (fp32),
+ *   dfmap1[b,c,h,w1] = (sum_w2 G[(b,h,w1),w2] * fmap2[b,c,h,w2]) / denom
+ *   dfmap2[b,c,h,w2] = (sum_w1 G[(b,h,w1),w2] * fmap1[b,c,h,w1]) / denom
+ * i.e. the autograd of core/corr.py:154-156 (einsum, then / sqrt(D)).  fp32 NCHW feature maps and
+ * outputs; W1 and W2 must be multiples of 4 (TMA 16-byte strides) -- SMOE_ERR_UNSUPPORTED otherwise.
+ */
+int smoe_corr_build_bwd(const void* fmap1, const void* fmap2, int in_dtype, int B, int C, int H,
+                        int W1, int W2, const smoe_pyramid_t* grad_pyr, float denom, void* dfmap1,
+                        void* dfmap2, smoe_stream_t stream);
 
 /*
  * Debug aid (not part of the reference interface): when a device buffer of

@@ -24,7 +24,7 @@ SYMBOLS = (
     "smoe_corr_abi_version", "smoe_corr_last_error", "smoe_corr_device_supported",
     "smoe_corr_pyramid_layout", "smoe_corr_build_workspace_bytes", "smoe_corr_build",
     "smoe_corr_lookup", "smoe_corr_lookup_bwd", "smoe_corr_fold_pyramid_grad",
-    "smoe_corr_debug_set_timeline",
+    "smoe_corr_debug_set_timeline", "smoe_corr_build_bwd",
 )
 
 
@@ -62,6 +62,8 @@ def _declare(L: ctypes.CDLL) -> None:
     L.smoe_corr_lookup.argtypes = [pp, vp, i64, f32, i32, vp, i32, vp]
     L.smoe_corr_lookup_bwd.argtypes = [pp, vp, i64, f32, i32, vp, i32, i32, vp]
     L.smoe_corr_fold_pyramid_grad.argtypes = [pp, vp]
+    L.smoe_corr_build_bwd.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, pp, f32, vp, vp, vp]
+    L.smoe_corr_build_bwd.restype = i32
     L.smoe_corr_debug_set_timeline.argtypes = [vp]
     L.smoe_corr_debug_set_timeline.restype = None
     for name in ("smoe_corr_pyramid_layout", "smoe_corr_build", "smoe_corr_lookup",

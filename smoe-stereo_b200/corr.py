@@ -110,6 +110,32 @@ def _build_into(pyr: FusedPyramid, fmap1: torch.Tensor, fmap2: torch.Tensor, fla
         ws.record_stream(torch.cuda.current_stream(fmap1.device))
 
 
+def _build_backward(gp: FusedPyramid, fmap1: torch.Tensor, fmap2: torch.Tensor):
+    """Autograd of core/corr.py:154-156 given the folded level-0 gradient in `gp`:
+    d fmap1 = G . fmap2^T / sqrt(C), d fmap2 = G^T . fmap1^T / sqrt(C)  (smoe_corr_build_bwd,
+    tcgen05 kind::tf32).  W not a multiple of 4 violates TMA's 16-byte stride rule for the NCHW
+    operands; those shapes (never produced by the model: images are padded to /32,
+    dataloader/utils.py:260-267) take the cuBLAS einsum instead."""
+    B, C, H, W1 = fmap1.shape
+    W2 = fmap2.shape[3]
+    f1 = fmap1.float().contiguous()
+    f2 = fmap2.float().contiguous()
+    if W1 % 4 == 0 and W2 % 4 == 0 and f1.data_ptr() % 16 == 0 and f2.data_ptr() % 16 == 0:
+        df1 = torch.empty_like(f1)
+        df2 = torch.empty_like(f2)
+        with _on_device(gp.device):
+            rc = _lib.lib().smoe_corr_build_bwd(f1.data_ptr(), f2.data_ptr(), _lib.DTYPE_F32, B, C, H, W1,
+                                                W2, gp.ref, math.sqrt(C), df1.data_ptr(), df2.data_ptr(),
+                                                _stream_ptr(gp.device))
+        _lib.check(rc, "smoe_corr_build_bwd")
+    else:
+        g0 = gp.level(0)                                    # (B,H,W1,W2) fp32, strided view
+        scale = 1.0 / math.sqrt(C)
+        df1 = torch.einsum("bhkw,bchw->bchk", g0, f2).mul_(scale)
+        df2 = torch.einsum("bhkw,bchk->bchw", g0, f1).mul_(scale)
+    return df1.to(fmap1.dtype), df2.to(fmap2.dtype)
+
+
 def _coords_plane(coords: torch.Tensor, B: int, H: int, W1: int):
     """Validate coords (B,>=1,H,W1) fp32 and return (tensor kept alive, batch stride in elements).
     Only channel 0 (x) is read (core/corr.py:129, :47)."""
@@ -172,15 +198,8 @@ class _BuildFn(torch.autograd.Function):
         with _on_device(gp.device):
             rc = _lib.lib().smoe_corr_fold_pyramid_grad(gp.ref, _stream_ptr(gp.device))
         _lib.check(rc, "smoe_corr_fold_pyramid_grad")
-        # Autograd of core/corr.py:154-156.  The two backward GEMMs still go through cuBLAS
-        # (native tcgen05 build-backward is the next widening step).
-        g0 = gp.level(0)                                    # (B,H,W1,W2) fp32, strided view
-        scale = 1.0 / math.sqrt(fmap1.shape[1])
-        f1 = fmap1.float()
-        f2 = fmap2.float()
-        df1 = torch.einsum("bhkw,bchw->bchk", g0, f2).mul_(scale)
-        df2 = torch.einsum("bhkw,bchk->bchw", g0, f1).mul_(scale)
-        return df1.to(fmap1.dtype), df2.to(fmap2.dtype), None
+        df1, df2 = _build_backward(gp, fmap1, fmap2)
+        return df1, df2, None
 
 
 class _LookupFn(torch.autograd.Function):

@@ -426,7 +426,9 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static EncodeTiledFn encode_fn() {
+EncodeTiledFn tensor_map_encoder();   // shared with build_bwd.cu
+static EncodeTiledFn encode_fn() { return tensor_map_encoder(); }
+EncodeTiledFn tensor_map_encoder() {
   static EncodeTiledFn fn = [] {
     void* p = nullptr;
     cudaDriverEntryPointQueryResult q;

@@ -58,6 +58,15 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst_smem, const void* tmap,
       ::"r"(dst_smem), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// 3-D tiled load global -> shared
+__device__ __forceinline__ void tma_load_3d(uint32_t dst_smem, const void* tmap, uint32_t bar, int c0,
+                                            int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst_smem), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 // 3-D tiled store shared -> global (bulk async group)
 __device__ __forceinline__ void tma_store_3d(const void* tmap, uint32_t src_smem, int c0, int c1,
                                              int c2) {

@@ -121,3 +121,28 @@ def test_bwd_linearity_and_adjoint_full_size(sb):
     _bwd_acc(sb, gp2, coords, 2 * gout, 4)
     _bwd_acc(sb, gp, coords, gout, 4)          # accumulate twice == once with 2x
     assert torch.equal(gp.buffer, gp2.buffer)
+
+
+@pytest.mark.parametrize("shape", [
+    (2, 256, 5, 184, 184),     # BASELINE config 2 width (training crop 320x736)
+    (1, 256, 3, 240, 240),     # config 1 width
+    (1, 100, 2, 72, 136),      # C not a multiple of 16, W1 != W2, K tails
+    (1, 300, 2, 40, 312),      # C > 256 -> two N tiles; W2 > 256 -> three M tiles in GEMM 1
+])
+def test_native_build_backward_vs_oracle(sb, oracle, shape):
+    """smoe_corr_build_bwd (tcgen05 tf32) == autograd of the einsum (core/corr.py:154-156)."""
+    from gpu_util import dev
+    from smoe_stereo_b200.corr import _build_backward
+    B, C, H, W1, W2 = shape
+    rs = np.random.RandomState(C + W1)
+    f1 = rs.standard_normal((B, C, H, W1)).astype(np.float32)
+    f2 = rs.standard_normal((B, C, H, W2)).astype(np.float32)
+    G = rs.standard_normal((B, H, W1, W2)).astype(np.float32)
+    want1, want2 = oracle.c_corr_volume_bwd(f1, f2, G)
+    gp = sb.FusedPyramid(B, H, W1, W2, 4, torch.float32, dev())
+    gp.buffer.fill_(float("nan"))                    # padding / coarser levels must never be read
+    gp.level(0).copy_(torch.from_numpy(G).to(dev()))
+    df1, df2 = _build_backward(gp, torch.from_numpy(f1).to(dev()), torch.from_numpy(f2).to(dev()))
+    e1, e2 = rel_max(df1.cpu().numpy(), want1), rel_max(df2.cpu().numpy(), want2)
+    print(f"[build_bwd {shape}] rel_max d fmap1 {e1:.2e}, d fmap2 {e2:.2e}")
+    assert e1 < E2E_GRAD_TOL and e2 < E2E_GRAD_TOL
