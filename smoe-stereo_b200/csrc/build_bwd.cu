@@ -11,7 +11,10 @@
 //   F^T as B (N = c, K = w): K-major (w contiguous in NCHW) -> SWIZZLE_128B, box {32 k, 1, 256 c, 1}
 // The accumulator tile is [128 (w) x 256 (c)]: TMEM lane = w, column = c, so for a fixed channel
 // the 32 lanes of a warp hold 32 consecutive w -- exactly the contiguous axis of the NCHW output:
-// every global store in the epilogue is one full 128-byte line, no staging needed.
+// a warp's [32 c x 32 w] sub-tile is staged in shared memory with conflict-free stores (lane = w)
+// and written by ONE TMA tensor store (box {32 w, 1, 32 c, 1} on the NCHW gradient, tails clipped).
+// (A first version issued 32 scalar global stores per chunk with per-store 64-bit address math:
+// ~740 instructions per chunk on one warp per scheduler, 3x slower -- profiles/r01/README.md.)
 // Same warp roles / mbarrier pipeline as corr_build_kernel (build.cu).
 #include <cuda.h>
 #include <math.h>
@@ -26,7 +29,8 @@ constexpr int kBwdABytes = kBwdM * kBwdKT * 4;    // 16 KB
 constexpr int kBwdBBytes = kBwdN * kBwdKT * 4;    // 32 KB
 constexpr int kBwdStageBytes = kBwdABytes + kBwdBBytes;
 constexpr int kBwdThreads = 192;
-constexpr size_t kBwdSmemBytes = (size_t)kBwdStages * kBwdStageBytes + 1024;
+constexpr int kBwdStgBytes = 32 * 128;             // staging tile: 32 channels x 32 w (128 bytes)
+constexpr size_t kBwdSmemBytes = (size_t)kBwdStages * kBwdStageBytes + 4 * 2 * kBwdStgBytes + 1024;
 
 struct BwdDims {
   int W1, W2, C, H, BH;
@@ -55,7 +59,9 @@ corr_build_bwd_kernel(const __grid_constant__ CUtensorMap map_gk,   // G, K-majo
                       const __grid_constant__ CUtensorMap map_gm,   // G, MN-major slabs (GEMM 1 A)
                       const __grid_constant__ CUtensorMap map_f1,   // fmap1 as B of GEMM 1
                       const __grid_constant__ CUtensorMap map_f2,   // fmap2 as B of GEMM 0
-                      float* __restrict__ df1, float* __restrict__ df2, const BwdDims dims) {
+                      const __grid_constant__ CUtensorMap map_d1,   // d fmap1 (W1,H,C,B), store
+                      const __grid_constant__ CUtensorMap map_d2,   // d fmap2 (W2,H,C,B), store
+                      const BwdDims dims) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t s_full[kBwdStages], s_empty[kBwdStages], s_tfull[2], s_tempty[2];
   __shared__ uint32_t s_tmem_base;
@@ -69,6 +75,8 @@ corr_build_bwd_kernel(const __grid_constant__ CUtensorMap map_gk,   // G, K-majo
     ptx::prefetch_tensormap(&map_gm);
     ptx::prefetch_tensormap(&map_f1);
     ptx::prefetch_tensormap(&map_f2);
+    ptx::prefetch_tensormap(&map_d1);
+    ptx::prefetch_tensormap(&map_d2);
     for (int i = 0; i < kBwdStages; ++i) {
       ptx::mbar_init(ptx::smem_u32(&s_full[i]), 1);
       ptx::mbar_init(ptx::smem_u32(&s_empty[i]), 1);
@@ -172,35 +180,47 @@ corr_build_bwd_kernel(const __grid_constant__ CUtensorMap map_gk,   // G, K-majo
   } else {
     // ---------------------------------------------------------------------- epilogue
     const int quad = warp & 3;
+    const uint32_t stg_base = smem_base + kBwdStages * kBwdStageBytes + (uint32_t)(warp - 2) * 2 * kBwdStgBytes;
     int buf = 0;
     uint32_t bphase = 0;
+    int stg_sel = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       const BwdItem it = decode_item(item, dims);
       const int b = it.bh / dims.H, h = it.bh - b * dims.H;
       const int Wm = it.which ? dims.W2 : dims.W1;
-      const int m = it.mt * kBwdM + quad * 32 + lane;
+      const int m0 = it.mt * kBwdM + quad * 32;          // first w of this warp's 32 rows
       const int n_valid = min(kBwdN, dims.C - it.nt * kBwdN);
-      float* out = (it.which ? df2 : df1) +
-                   (((long long)b * dims.C + (long long)it.nt * kBwdN) * dims.H + h) * Wm + m;
-      const long long cstride = (long long)dims.H * Wm;
+      const CUtensorMap* omap = it.which ? &map_d2 : &map_d1;
       ptx::mbar_wait(ptx::smem_u32(&s_tfull[buf]), bphase);
       ptx::tc_fence_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)buf * kBwdN;
       for (int c0 = 0; c0 < n_valid; c0 += 32) {
+        const uint32_t stg = stg_base + (uint32_t)stg_sel * kBwdStgBytes;
+        if (lane == 0) ptx::tma_store_wait_read<1>();     // staging buffer of two chunks ago drained
+        __syncwarp();
         uint32_t acc[32];
         ptx::tmem_ld_32x32(taddr + c0, acc);
         ptx::tmem_ld_wait();
-        if (m < Wm) {
+        // staging tile [32 c][32 w]: lane = w, so each store instruction covers one 128-byte row
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (c0 + j < n_valid) out[(long long)(c0 + j) * cstride] = __uint_as_float(acc[j]) * dims.scale;
+        for (int j = 0; j < 32; ++j)
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(stg + j * 128 + lane * 4),
+                       "f"(__uint_as_float(acc[j]) * dims.scale)
+                       : "memory");
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (m0 < Wm) ptx::tma_store_4d(omap, stg, m0, h, it.nt * kBwdN + c0, b);
+          ptx::tma_store_commit();
         }
+        stg_sel ^= 1;
       }
       ptx::tc_fence_before_sync();
       ptx::mbar_arrive(ptx::smem_u32(&s_tempty[buf]));
       buf ^= 1;
       if (buf == 0) bphase ^= 1u;
     }
+    if (lane == 0) ptx::tma_store_wait_all<0>();
   }
 
   ptx::tc_fence_before_sync();
@@ -219,11 +239,13 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 EncodeTiledFn tensor_map_encoder();   // build.cu
 
 static int encode(CUtensorMap* out, int rank, const void* base, const cuuint64_t* gdim,
-                  const cuuint64_t* gstr, const cuuint32_t* box, CUtensorMapSwizzle sw, const char* what) {
+                  const cuuint64_t* gstr, const cuuint32_t* box, CUtensorMapSwizzle sw, const char* what,
+                  bool tf32 = true) {
   EncodeTiledFn enc = tensor_map_encoder();
   SMOE_REQUIRE(enc != nullptr, SMOE_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
-  const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, (cuuint32_t)rank, const_cast<void*>(base),
+  const CUresult r = enc(out, tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                         (cuuint32_t)rank, const_cast<void*>(base),
                          gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SMOE_REQUIRE(r == CUDA_SUCCESS, SMOE_ERR_CUDA, "cuTensorMapEncodeTiled(%s) failed with CUresult %d", what,
@@ -275,6 +297,17 @@ int smoe_corr_build_bwd(const void* fmap1, const void* fmap2, int in_dtype, int 
   };
   if (int rc = fmap_map(&f1m, fmap1, W1, "fmap1")) return rc;
   if (int rc = fmap_map(&f2m, fmap2, W2, "fmap2")) return rc;
+  CUtensorMap d1m, d2m;
+  auto out_map = [&](CUtensorMap* m, void* base, int W, const char* what) {
+    const cuuint64_t gdim[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)B};
+    const cuuint64_t gstr[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)C * H * W * 4};
+    const cuuint32_t box[4] = {32u, 1u, 32u, 1u};
+    return encode(m, 4, base, gdim, gstr, box, CU_TENSOR_MAP_SWIZZLE_NONE, what, false);
+  };
+  SMOE_REQUIRE(aligned16(dfmap1) && aligned16(dfmap2), SMOE_ERR_INVALID_ARG,
+               "build_bwd: gradient outputs must be 16-byte aligned");
+  if (int rc = out_map(&d1m, dfmap1, W1, "dfmap1")) return rc;
+  if (int rc = out_map(&d2m, dfmap2, W2, "dfmap2")) return rc;
 
   BwdDims d;
   d.W1 = W1; d.W2 = W2; d.C = C; d.H = H; d.BH = B * H;
@@ -292,8 +325,7 @@ int smoe_corr_build_bwd(const void* fmap1, const void* fmap2, int in_dtype, int 
   SMOE_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = (int)(items < sms ? items : sms);
   SMOE_CUDA_OK(launch_kernel(corr_build_bwd_kernel, dim3(grid), dim3(kBwdThreads), kBwdSmemBytes,
-                             static_cast<cudaStream_t>(stream), gk, gm, f1m, f2m,
-                             static_cast<float*>(dfmap1), static_cast<float*>(dfmap2), d));
+                             static_cast<cudaStream_t>(stream), gk, gm, f1m, f2m, d1m, d2m, d));
   return check_launch("corr_build_bwd_kernel");
 }
 

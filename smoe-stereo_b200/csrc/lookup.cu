@@ -334,29 +334,76 @@ lookup_bwd_dense_kernel(PyrDev gp, const float* __restrict__ coords, long long c
 // ----------------------------------------------------------------------------------- fold
 // G0[j] += 0.5*(G1[j/2] + 0.5*(G2[j/4] + 0.5*G3[j/8])), stopping at the first level whose index
 // falls outside its width (the column an odd level dropped, core/corr.py:124).
+// Vector kernel: one thread owns 4 consecutive level-0 columns (they share G2[j/4], G3[j/8] and
+// use G1[j/2], G1[j/2+1]) and processes kFoldUnroll such groups with all loads issued up front.
+constexpr int kFoldUnroll = 4;
+
 __global__ void __launch_bounds__(256)
-fold_grad_kernel(PyrDev gp, long long rows) {
+fold_grad_vec_kernel(PyrDev gp, unsigned total_vecs, unsigned vecs_per_row) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int w1 = gp.num_levels > 1 ? gp.width[1] : 0;
+  const int w2 = gp.num_levels > 2 ? gp.width[2] : 0;
+  const int w3 = gp.num_levels > 3 ? gp.width[3] : 0;
+  const unsigned base = blockIdx.x * (256u * kFoldUnroll) + threadIdx.x;
+  float4 g0[kFoldUnroll];
+  float2 g1[kFoldUnroll];
+  float g2[kFoldUnroll], g3[kFoldUnroll];
+  float4* dst[kFoldUnroll];
+  int jj[kFoldUnroll];
+#pragma unroll
+  for (int u = 0; u < kFoldUnroll; ++u) {
+    const unsigned idx = base + u * 256u;
+    dst[u] = nullptr;
+    if (idx < total_vecs) {
+      const unsigned row = idx / vecs_per_row;
+      const int j = (int)(idx - row * vecs_per_row) * 4;
+      jj[u] = j;
+      dst[u] = reinterpret_cast<float4*>(static_cast<float*>(gp.ptr[0]) + (long long)row * gp.pitch[0] + j);
+      g0[u] = __ldcg(dst[u]);
+      const int m = j >> 1, q = j >> 2, o = j >> 3;
+      const float* p1 = static_cast<const float*>(gp.ptr[1]) + (long long)row * gp.pitch[1] + m;
+      g1[u].x = m < w1 ? __ldg(p1) : 0.f;
+      g1[u].y = m + 1 < w1 ? __ldg(p1 + 1) : 0.f;
+      g2[u] = q < w2 ? __ldg(static_cast<const float*>(gp.ptr[2]) + (long long)row * gp.pitch[2] + q) : 0.f;
+      g3[u] = (q < w2 && o < w3) ? __ldg(static_cast<const float*>(gp.ptr[3]) + (long long)row * gp.pitch[3] + o) : 0.f;
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < kFoldUnroll; ++u) {
+    if (dst[u] == nullptr) continue;
+    const int m = jj[u] >> 1, q = jj[u] >> 2;
+    const float c2 = q < w2 ? g2[u] + 0.5f * g3[u] : 0.f;            // t = g2 + 0.5*g3
+    const float a0 = m < w1 ? 0.5f * (g1[u].x + 0.5f * c2) : 0.f;    // 0.5*(g1 + 0.5*t)
+    const float a1 = m + 1 < w1 ? 0.5f * (g1[u].y + 0.5f * c2) : 0.f;
+    float4 v = g0[u];
+    v.x += a0; v.y += a0; v.z += a1; v.w += a1;
+    __stcg(dst[u], v);
+  }
+}
+
+// Scalar fallback for unaligned level-0 widths / pitches: one warp per pixel row.
+__global__ void __launch_bounds__(256)
+fold_grad_scalar_kernel(PyrDev gp, long long rows) {
   pdl_launch_dependents();
   pdl_wait();
   const int w0 = gp.width[0];
-  const long long total = rows * w0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long row = i / w0;
-    const int j = static_cast<int>(i - row * w0);
-    int top = 0;
-    for (int l = 1; l < gp.num_levels; ++l) {
-      if ((j >> l) >= gp.width[l]) break;
-      top = l;
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long row = warp0; row < rows; row += nwarps) {
+    float* g0 = static_cast<float*>(gp.ptr[0]) + row * gp.pitch[0];
+    for (int j = lane; j < w0; j += 32) {
+      int top = 0;
+      for (int l = 1; l < gp.num_levels; ++l) {
+        if ((j >> l) >= gp.width[l]) break;
+        top = l;
+      }
+      float t = 0.f;
+      for (int l = top; l >= 1; --l)
+        t = __ldg(static_cast<const float*>(gp.ptr[l]) + row * gp.pitch[l] + (j >> l)) + 0.5f * t;
+      g0[j] += 0.5f * t;
     }
-    if (top == 0) continue;
-    float t = 0.f;
-    for (int l = top; l >= 1; --l) {
-      const float gl = static_cast<const float*>(gp.ptr[l])[row * gp.pitch[l] + (j >> l)];
-      t = gl + 0.5f * t;
-    }
-    float* g0 = static_cast<float*>(gp.ptr[0]) + row * gp.pitch[0] + j;
-    *g0 += 0.5f * t;
   }
 }
 
@@ -569,11 +616,20 @@ int smoe_corr_fold_pyramid_grad(const smoe_pyramid_t* gp, smoe_stream_t stream) 
                "fold_pyramid_grad: gradient pyramid must be fp32");
   const long long rows = (long long)gp->B * gp->H * gp->W1;
   if (rows == 0 || gp->width[0] == 0 || gp->num_levels == 1) return SMOE_OK;
-  const long long total = rows * gp->width[0];
-  long long blocks = (total + 255) / 256;
-  if (blocks > 148ll * 32) blocks = 148ll * 32;
-  launch_kernel(fold_grad_kernel, dim3((unsigned)blocks), dim3(256), 0, static_cast<cudaStream_t>(stream),
-                to_dev(gp), rows);
+  const long long vpr = gp->width[0] / 4;
+  const bool vec = gp->width[0] % 4 == 0 && aligned16(gp->level_ptr[0]) && (gp->pitch[0] % 4) == 0 &&
+                   rows * vpr < (1ll << 31);
+  if (vec) {
+    const long long total = rows * vpr;
+    const long long blocks = (total + 256 * kFoldUnroll - 1) / (256 * kFoldUnroll);
+    launch_kernel(fold_grad_vec_kernel, dim3((unsigned)blocks), dim3(256), 0,
+                  static_cast<cudaStream_t>(stream), to_dev(gp), (unsigned)total, (unsigned)vpr);
+  } else {
+    long long blocks = (rows + 7) / 8;          // 8 warps (rows) per block
+    if (blocks > 148ll * 8) blocks = 148ll * 8;
+    launch_kernel(fold_grad_scalar_kernel, dim3((unsigned)blocks), dim3(256), 0,
+                  static_cast<cudaStream_t>(stream), to_dev(gp), rows);
+  }
   return check_launch("fold_pyramid_grad");
 }
 
