@@ -52,7 +52,6 @@ lookup_fwd_vec_kernel(PyrDev pyr, const float* __restrict__ coords, long long co
   __shared__ __align__(16) float s_win[NL][TPX * Tile::kStride];
   __shared__ int s_shift[NL][TPX];
 
-  pdl_launch_dependents();   // successors may become resident; they block in their own pdl_wait
   pdl_wait();                // coords / pyramid come from earlier kernels in the stream
   const int tid = threadIdx.x;
   const int p = tid >> 2, q = tid & 3;
@@ -89,6 +88,7 @@ lookup_fwd_vec_kernel(PyrDev pyr, const float* __restrict__ coords, long long co
       }
     }
   }
+  pdl_launch_dependents();   // all loads are in flight: let the successor's CTAs become resident
 #pragma unroll
   for (int l = 0; l < NL; ++l) {
     const float nxt = __shfl_down_sync(0xffffffffu, v[l][0], 1);   // first element of chunk q+1
