@@ -331,12 +331,24 @@ def main():
         return {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                 "traffic": traffic, "us_per_launch": secs * 1e6, "algorithmic_bytes": bytes_, "peak_source": peak_src}
 
-    roofline = roof(lookup_bytes, t_lookup)
-    roofline["kernel"] = "lookup_fwd_vec_kernel<float,float,4,4>"
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01", "traffic.json")))
+    except Exception:           # noqa: BLE001
+        pass
+
+    def ncu_traffic(key):
+        t = traffic.get(key) if args.workload == "cfg1" else None
+        return (t["read"] + t["write"]) if t else None
+
+    roofline = roof(lookup_bytes, t_lookup, ncu_traffic("lookup_fwd_vec_kernel<float,float,4,4,32,false>@cfg1"))
+    roofline["kernel"] = "lookup_fwd_vec_kernel<float,float,4,4,32,false>"
+    roofline["traffic_note"] = ("ncu cold-cache replay (profiles/r01/ncu_lookup_cfg1.txt); inside the timed step the "
+                                "pyramid is L2-resident and DRAM traffic is ~0")
     roofline["note"] = ("pyramid of this workload (%.0f MB) fits the 126 MB L2: bandwidth is L2-assisted and the "
                         "kernel is launch/latency-bound at this size" % (B * H * W * pitch * 4 / 1e6)
                         if B * H * W * pitch * 4 < 126e6 else "pyramid exceeds L2: HBM-bound")
-    roofline_build = roof(build_bytes, t_build)
+    roofline_build = roof(build_bytes, t_build, ncu_traffic("corr_build_kernel<float,float>@cfg1"))
     roofline_build["kernel"] = "corr_build_kernel<float,float>"
     roofline_build["tensor_tflops"] = build_flops / t_build / 1e12
     roofline_build["tensor_frac_of_tf32_peak"] = build_flops / t_build / 1e12 / tf_peak
