@@ -1,0 +1,153 @@
+"""GPU: behaviour of the reference-facing classes beyond the golden cases -- level counts, radii,
+the "alt" alias, fp16 training path, streams, non-contiguous coords, the drop-in installer."""
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_names, load_golden, rel_max
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sb():
+    import smoe_stereo_b200 as m
+    assert torch.cuda.is_available()
+    return m
+
+
+@pytest.mark.parametrize("levels,radius", [(1, 4), (2, 4), (3, 4), (4, 2), (4, 5), (2, 7)])
+def test_levels_and_radii_vs_oracle(sb, oracle, levels, radius):
+    """num_levels 1..4 use the templated vector kernel (radius 4) or the generic one (others)."""
+    from gpu_util import dev, make_coords
+    B, C, H, W = 2, 64, 4, 96
+    rs = np.random.RandomState(levels * 10 + radius)
+    f1 = rs.standard_normal((B, C, H, W)).astype(np.float16).astype(np.float32)   # exact in tf32
+    f2 = rs.standard_normal((B, C, H, W)).astype(np.float16).astype(np.float32)
+    want_lv = oracle.c_pyramid(oracle.numpy_corr_volume(f1, f2), levels)
+    blk = sb.CorrBlock1D(torch.from_numpy(f1).to(dev()), torch.from_numpy(f2).to(dev()),
+                         num_levels=levels, radius=radius)
+    assert blk.num_levels == levels and blk.radius == radius and len(blk.corr_pyramid) == levels
+    coords = make_coords(B, H, W, W, 2, seed=5)
+    for t in range(2):
+        out = blk(torch.from_numpy(coords[t]).to(dev()))
+        assert tuple(out.shape) == (B, levels * (2 * radius + 1), H, W)
+        want = oracle.c_lookup(want_lv, np.ascontiguousarray(coords[t]), radius)
+        assert rel_max(out.cpu().numpy(), want) < 5e-6
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if n != "w1_ne_w2"])
+def test_alt_block_matches_reference_alt_output(sb, name):
+    from gpu_util import dev
+    g = load_golden(name)
+    d = g["dims"]
+    alt = sb.PytorchAlternateCorrBlock1D(torch.from_numpy(g["f1"]).to(dev()),
+                                         torch.from_numpy(g["f2"]).to(dev()),
+                                         num_levels=d["L"], radius=d["r"])
+    out = alt(torch.from_numpy(g["coords"][0]).to(dev()))
+    assert out.dtype == torch.float32
+    assert rel_max(out.cpu().numpy(), g["out_alt"]) < 1e-3      # core/corr.py:64-107
+    assert alt.fmap1 is not None and alt.fmap2 is not None
+
+
+def test_fast_block_fp16_training_path(sb):
+    """reg_cuda under autocast: fp16 features, fp16 lookups, gradients flow back in fp16."""
+    from gpu_util import dev, make_coords
+    B, C, H, W = 1, 64, 4, 64
+    g = torch.Generator(device="cpu").manual_seed(3)
+    f1 = torch.randn(B, C, H, W, generator=g).half().to(dev()).requires_grad_(True)
+    f2 = torch.randn(B, C, H, W, generator=g).half().to(dev()).requires_grad_(True)
+    r1 = f1.detach().float().requires_grad_(True)
+    r2 = f2.detach().float().requires_grad_(True)
+    coords = torch.from_numpy(make_coords(B, H, W, W, 1, seed=2)[0]).to(dev())
+    gout = torch.randn(B, 36, H, W, generator=g).to(dev())
+    out16 = sb.CorrBlockFast1D(f1, f2)(coords)
+    assert out16.dtype == torch.float16 and out16.requires_grad
+    (out16.float() * gout).sum().backward()
+    out32 = sb.CorrBlock1D(r1, r2)(coords)
+    (out32 * gout).sum().backward()
+    assert f1.grad.dtype == torch.float16
+    assert rel_max(out16.float().detach().cpu().numpy(), out32.detach().cpu().numpy()) < 3e-3
+    assert rel_max(f1.grad.float().cpu().numpy(), r1.grad.cpu().numpy()) < 5e-3
+    assert rel_max(f2.grad.float().cpu().numpy(), r2.grad.cpu().numpy()) < 5e-3
+
+
+def test_no_grad_and_detached_inputs_skip_autograd(sb):
+    from gpu_util import dev
+    f = torch.randn(1, 32, 2, 32, device=dev(), requires_grad=True)
+    coords = torch.zeros(1, 2, 2, 32, device=dev())
+    with torch.no_grad():
+        out = sb.CorrBlock1D(f, f)(coords)
+    assert not out.requires_grad
+    out = sb.CorrBlock1D(f.detach(), f.detach())(coords)
+    assert not out.requires_grad
+
+
+def test_side_stream_and_noncontiguous_coords(sb, oracle):
+    from gpu_util import dev
+    B, C, H, W = 2, 32, 3, 40
+    rs = np.random.RandomState(0)
+    f1 = rs.standard_normal((B, C, H, W)).astype(np.float16).astype(np.float32)
+    f2 = rs.standard_normal((B, C, H, W)).astype(np.float16).astype(np.float32)
+    x = (np.arange(W, dtype=np.float32) - rs.uniform(0, 9, size=(B, H, W))).astype(np.float32)
+    levels = oracle.c_pyramid(oracle.numpy_corr_volume(f1, f2), 4)
+    want = oracle.c_lookup(levels, np.ascontiguousarray(x[:, None]), 4)
+    big = torch.zeros(B, 5, H, W, device=dev())
+    big[:, 2] = torch.from_numpy(x).to(dev())
+    s = torch.cuda.Stream(dev())
+    s.wait_stream(torch.cuda.current_stream(dev()))
+    with torch.cuda.stream(s):
+        blk = sb.CorrBlock1D(torch.from_numpy(f1).to(dev()), torch.from_numpy(f2).to(dev()))
+        out_slice = blk(big[:, 2:4])                 # batch stride 5*H*W, channel 0 of the view = x
+        out_perm = blk(big.permute(0, 1, 3, 2)[:, 2:3].permute(0, 1, 3, 2))
+        out_f64 = blk(big[:, 2:3].double())
+    s.synchronize()
+    for o in (out_slice, out_perm, out_f64):
+        assert rel_max(o.cpu().numpy(), want) < 5e-6
+
+
+def test_install_serves_reference_style_callers(sb):
+    """A module written the way core/corr.py:17-51 uses the extension (bare `import corr_sampler`,
+    `corr, = corr_sampler.forward(...)`) runs on this implementation after install()."""
+    from gpu_util import dev
+    fake = types.ModuleType("core.corr")
+    exec("import torch\n"
+         "def lookup(vol, coords, r):\n"
+         "    import corr_sampler\n"
+         "    corr, = corr_sampler.forward(vol, coords, r)\n"
+         "    return corr\n", fake.__dict__)
+    fake.CorrBlock1D = object
+    sys.modules["core.corr"] = fake
+    try:
+        replaced = sb.install()
+        assert "core.corr.CorrBlock1D" in replaced and fake.CorrBlock1D is sb.CorrBlock1D
+        vol = torch.randn(1, 2, 16, 32, device=dev())
+        coords = torch.rand(1, 1, 2, 16, device=dev()) * 30
+        got = fake.lookup(vol, coords, 4)
+        want, = sb.corr_sampler.forward(vol, coords, 4)
+        assert torch.equal(got, want)
+    finally:
+        sb.uninstall()
+        sys.modules.pop("core.corr", None)
+
+
+def test_sharded_block_single_process_equals_full(sb):
+    from gpu_util import dev
+    f1 = torch.randn(2, 32, 6, 48, device=dev())
+    f2 = torch.randn(2, 32, 6, 48, device=dev())
+    coords = torch.zeros(2, 2, 6, 48, device=dev())
+    coords[:, 0] = torch.arange(48, device=dev()).float() - 3.7
+    full = sb.CorrBlock1D(f1, f2)(coords)
+    for mode in ("batch", "rows"):
+        blk = sb.ShardedCorrBlock1D(f1, f2, mode=mode)
+        assert torch.equal(blk(coords, gather=True), full)
+    # manual 2-way row shard, as two ranks would hold it: bit-identical to the full result
+    parts = []
+    for r in range(2):
+        lo, hi = sb.shard_bounds(6, 2, r)
+        b = sb.CorrBlock1D(f1[:, :, lo:hi].contiguous(), f2[:, :, lo:hi].contiguous())
+        parts.append(b(coords[:, :, lo:hi].contiguous()))
+    assert torch.equal(torch.cat(parts, dim=2), full)
