@@ -120,6 +120,11 @@ int smoe_corr_build(const void* fmap1, const void* fmap2, int in_dtype, int B, i
  *   out[b, i*(2r+1)+k, y, x] = (1-dx)*L_i[row, fl-r+k] + dx*L_i[row, fl-r+k+1],
  *   fl = floor(xi), dx = xi - fl, taps outside [0, W2_i) contribute 0.
  * coords_batch_stride = elements between batches of coords (coords_ch*H*W1).
+ * With more than one level the levels must form a pyramid as smoe_corr_build writes it (level
+ * i+1 == pair average of level i): for volumes larger than L2 the kernel reads one level-0 and
+ * one level-2 segment per pixel and recomputes the level-1 / level-3 taps from them with the
+ * same fp32 arithmetic (bit-identical).  Single-level calls (corr_sampler.forward) read exactly
+ * the level they are given.
  * out_dtype fp32, or fp16 for an fp16 pyramid (arithmetic then follows the reference's
  * half-precision accumulation order, sampler_kernel.cu:46-59).
  */

@@ -121,6 +121,135 @@ lookup_fwd_vec_kernel(PyrDev pyr, const float* __restrict__ coords, long long co
   }
 }
 
+// ------------------------------------------------------------------------- forward (level pairs)
+// Level i+1 is by construction the pair-average of level i (core/corr.py:122-125), and the 2r+2
+// taps of a pixel at level i+1 cover level-i indices [2*base_c, 2*base_c + 4r+3], which CONTAIN
+// the pixel's level-i window.  So the lookup reads ONE contiguous level-i segment (20 elements
+// for r=4) per level pair (0,1) and (2,3) -- half the scattered DRAM accesses and fewer sectors
+// than four separate 10-element windows -- and recomputes the coarse taps as (a+b)*0.5f, the same
+// fp32 operation the build epilogue used, so the result is bit-identical to reading levels 1/3.
+// 8 lanes per pixel: lane q fetches aligned chunk q of both segments (<= 6 chunks for fp32,
+// <= 4 for fp16).  Window-space tiles + read-side shifts as in lookup_fwd_vec_kernel.
+template <typename VT, typename OT, int R, int NP, int TPX, bool STREAM>
+__global__ void __launch_bounds__(8 * TPX)
+lookup_fwd_pair_kernel(PyrDev pyr, const float* __restrict__ coords, long long coords_bstride,
+                       float coord_scale, OT* __restrict__ out, int HW) {
+  constexpr int EPL = Vec16<VT>::N;
+  constexpr int LOG_EPL = (EPL == 4) ? 2 : 3;
+  constexpr int RD = 2 * R + 1;
+  constexpr int SEG = 4 * R + 4;                              // fine elements under the coarse window
+  constexpr int NCH = (EPL - 2 + SEG + EPL - 1) / EPL;        // chunks a segment can span
+  static_assert(NCH <= 8, "segment must fit the 8 lanes of a pixel");
+  constexpr int FW = 8 * EPL;                                 // fine window-space words per pixel
+  constexpr int FS = FW + 4;                                  // row stride (bank spreading)
+  constexpr int CW = 4 * EPL;                                 // coarse window-space words per pixel
+  constexpr int CS = CW + 4;
+  __shared__ __align__(16) float s_fine[NP][TPX * FS];
+  __shared__ __align__(16) float s_coarse[NP][TPX * CS];
+  __shared__ int s_shift[2 * NP][TPX];
+
+  pdl_wait();
+  const int tid = threadIdx.x;
+  const int p = tid >> 3, q = tid & 7;
+  const int b = blockIdx.y;
+  const int hw0 = blockIdx.x * TPX;
+  const int hw = hw0 + p;
+  const bool valid = hw < HW;
+  const float x0 = valid ? __ldg(coords + (long long)b * coords_bstride + hw) * coord_scale : 0.f;
+  const long long row = (long long)b * HW + hw;
+
+  float v[NP][EPL];
+  float dxf[NP], dxc[NP];
+  int ci0[NP];
+  float lscale = 1.0f;
+#pragma unroll
+  for (int pr = 0; pr < NP; ++pr) {
+    const int lf = 2 * pr;
+    int basef, basec;
+    split_coord(x0 * lscale, R, basef, dxf[pr]);
+    split_coord(x0 * lscale * 0.5f, R, basec, dxc[pr]);
+    lscale *= 0.25f;
+    // the segment follows the coarse window unless the coordinate is out of the representable
+    // range (split_coord parks both far outside, everything masks to zero)
+    const int S = 2 * basec;
+    const int cs = S >> LOG_EPL;                               // first chunk of the segment
+    const int ci = cs + q;
+    ci0[pr] = cs;
+    if (q == 0) {
+      s_shift[2 * pr][p] = basef - (cs << LOG_EPL);            // fine tap k  -> fine tile index
+      s_shift[2 * pr + 1][p] = basec - (cs << (LOG_EPL - 1));  // coarse tap k -> coarse tile index
+    }
+    const int width = pyr.width[lf];
+    const int nchunks = (width + EPL - 1) >> LOG_EPL;
+    const bool need = valid && q < NCH && (ci << LOG_EPL) < S + SEG && ci >= 0 && ci < nchunks;
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) v[pr][j] = 0.f;
+    if (need) {
+      const VT* src = static_cast<const VT*>(pyr.ptr[lf]) + row * pyr.pitch[lf] + (long long)ci * EPL;
+      Vec16<VT>::template load<STREAM>(src, v[pr]);
+      if ((ci + 1) * EPL > width) {
+#pragma unroll
+        for (int j = 0; j < EPL; ++j)
+          if (ci * EPL + j >= width) v[pr][j] = 0.f;
+      }
+    }
+  }
+  pdl_launch_dependents();
+#pragma unroll
+  for (int pr = 0; pr < NP; ++pr) {
+    const int wc = (2 * pr + 1 < pyr.num_levels) ? pyr.width[2 * pr + 1] : 0;
+    const int ci = ci0[pr] + q;
+    // coarse values owned by this lane: pair averages, zero where the coarse level has no column
+    float pc[EPL / 2];
+#pragma unroll
+    for (int j = 0; j < EPL / 2; ++j) {
+      const int cidx = ci * (EPL / 2) + j;
+      float a = (v[pr][2 * j] + v[pr][2 * j + 1]) * 0.5f;
+      if (sizeof(VT) == 2) a = __half2float(__float2half_rn(a));     // stored level is fp16
+      pc[j] = (cidx >= 0 && cidx < wc) ? a : 0.f;
+    }
+    const float nxt_f = __shfl_down_sync(0xffffffffu, v[pr][0], 1);
+    const float nxt_c = __shfl_down_sync(0xffffffffu, pc[0], 1);
+    float ef[EPL], ec[EPL / 2];
+#pragma unroll
+    for (int j = 0; j < EPL; ++j)
+      ef[j] = to_float(lerp_ref<OT>(v[pr][j], (j + 1 < EPL) ? v[pr][j + 1] : nxt_f, dxf[pr]));
+#pragma unroll
+    for (int j = 0; j < EPL / 2; ++j)
+      ec[j] = to_float(lerp_ref<OT>(pc[j], (j + 1 < EPL / 2) ? pc[j + 1] : nxt_c, dxc[pr]));
+#pragma unroll
+    for (int h = 0; h < EPL / 4; ++h)
+      *reinterpret_cast<float4*>(&s_fine[pr][p * FS + (q * (EPL / 4) + h) * 4]) =
+          make_float4(ef[4 * h], ef[4 * h + 1], ef[4 * h + 2], ef[4 * h + 3]);
+    if (EPL == 4) {
+      *reinterpret_cast<float2*>(&s_coarse[pr][p * CS + q * 2]) = make_float2(ec[0], ec[1]);
+    } else {
+      *reinterpret_cast<float4*>(&s_coarse[pr][p * CS + q * 4]) =
+          make_float4(ec[0], ec[1], ec[EPL == 4 ? 0 : 2], ec[EPL == 4 ? 1 : 3]);
+    }
+  }
+  __syncthreads();
+  // output phase: lane = pixel; a warp takes one (level, 32-pixel group): full-line stores
+  const int warp = tid >> 5, lane = tid & 31;
+  constexpr int kGroups = TPX / 32, kWarps = TPX / 4;
+  const int NL = pyr.num_levels;
+  for (int item = warp; item < NL * kGroups; item += kWarps) {
+    const int l = item % NL, pg = item / NL;
+    const int pp = pg * 32 + lane;
+    if (hw0 + pp < HW) {
+      OT* dst = out + ((long long)b * (NL * RD) + l * RD) * HW + hw0 + pp;
+      const int sft = s_shift[l][pp];
+      const float* wrow = (l & 1) ? &s_coarse[l >> 1][pp * CS] : &s_fine[l >> 1][pp * FS];
+      const int lim = (l & 1) ? CW : FW;
+#pragma unroll
+      for (int k = 0; k < RD; ++k) {
+        const int e = sft + k;                                  // parked coordinates: out of tile -> 0
+        dst[(long long)k * HW] = from_float<OT>((e >= 0 && e < lim) ? wrow[e] : 0.f);
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------- forward (generic)
 template <typename VT, typename OT>
 __global__ void __launch_bounds__(128)
@@ -452,9 +581,35 @@ static void launch_fwd_vec(const PyrDev& d, const float* coords, long long cbs, 
 #undef SMOE_LAUNCH_FWD
 }
 
+static const bool g_no_pair = getenv("SMOE_CORR_NO_PAIR_LOOKUP") != nullptr;      // A/B switches
+static const bool g_force_pair = getenv("SMOE_CORR_FORCE_PAIR_LOOKUP") != nullptr;
+
+template <typename VT, typename OT, int NP>
+static void launch_fwd_pair(const PyrDev& d, const float* coords, long long cbs, float cs, void* out,
+                            int HW, int B, cudaStream_t st) {
+  constexpr int TPX = 32;
+  dim3 grid((HW + TPX - 1) / TPX, B);
+  const bool big = volume_exceeds_l2(d, (long long)HW * B, (int)sizeof(VT));
+  if (big)
+    launch_kernel(lookup_fwd_pair_kernel<VT, OT, 4, NP, TPX, true>, grid, dim3(8 * TPX), 0, st, d, coords,
+                  cbs, cs, static_cast<OT*>(out), HW);
+  else
+    launch_kernel(lookup_fwd_pair_kernel<VT, OT, 4, NP, TPX, false>, grid, dim3(8 * TPX), 0, st, d, coords,
+                  cbs, cs, static_cast<OT*>(out), HW);
+}
+
 template <typename VT, typename OT>
 static void dispatch_fwd_vec(int NL, const PyrDev& d, const float* coords, long long cbs, float cs,
                              void* out, int HW, int B, cudaStream_t st) {
+  // Volumes that stream from DRAM: two contiguous segments per pixel instead of four windows
+  // (cfg3: 31.3 -> 26.8 us).  L2-resident volumes stay on the 4-lane kernel (3.65 vs 4.04 us at
+  // cfg1: that regime is latency-bound and the pair kernel does more work per pixel).
+  const bool pair = volume_exceeds_l2(d, (long long)HW * B, (int)sizeof(VT)) || g_force_pair;
+  if (!g_no_pair && pair && (NL == 2 || NL == 4)) {
+    if (NL == 4) launch_fwd_pair<VT, OT, 2>(d, coords, cbs, cs, out, HW, B, st);
+    else launch_fwd_pair<VT, OT, 1>(d, coords, cbs, cs, out, HW, B, st);
+    return;
+  }
   switch (NL) {
     case 1: launch_fwd_vec<VT, OT, 1>(d, coords, cbs, cs, out, HW, B, st); break;
     case 2: launch_fwd_vec<VT, OT, 2>(d, coords, cbs, cs, out, HW, B, st); break;

@@ -107,8 +107,11 @@ def test_bwd_linearity_and_adjoint_full_size(sb):
     B, H, W = 8, 80, 184
     gen = torch.Generator(device="cpu").manual_seed(1)
     pyr = sb.FusedPyramid(B, H, W, W, 4, torch.float32, dev(), zero=True)
-    for i in range(4):
-        pyr.level(i).copy_(torch.randn(B, H, W, pyr.widths[i], generator=gen).to(dev()))
+    pyr.level(0).copy_(torch.randn(B, H, W, W, generator=gen).to(dev()))
+    for i in range(1, 4):        # a consistent pyramid (level i+1 = pair average), as the build writes it
+        w = pyr.widths[i]
+        prev = pyr.level(i - 1)
+        pyr.level(i).copy_((prev[..., 0:2 * w:2] + prev[..., 1:2 * w:2]) * 0.5)
     coords = torch.from_numpy(make_coords(B, H, W, W, 1, seed=3)[0]).to(dev())
     gout = torch.randn(B, 36, H, W, generator=gen).to(dev())
     out = _lookup(pyr, coords, 4, torch.float32)

@@ -105,3 +105,30 @@ def test_lookup_empty(sb):
     pyr = sb.FusedPyramid(0, 4, 8, 16, 4, torch.float32, dev())
     out = _lookup(pyr, torch.zeros(0, 2, 4, 8, device=dev()), 4, torch.float32)
     assert tuple(out.shape) == (0, 36, 4, 8)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_pair_kernel_equals_window_kernel_bitwise(sb, oracle, dtype, monkeypatch):
+    """Volumes beyond L2 take the level-pair kernel (two segments per pixel, coarse taps recomputed
+    on the fly).  On a consistent pyramid it must agree BIT FOR BIT with the 4-window kernel; a
+    260 MB volume (B=2, 120x260, fp32) crosses the size switch, the small one does not."""
+    from gpu_util import dev, make_coords
+    B, C, H, W = 2, 32, 120, 260
+    g = torch.Generator(device="cpu").manual_seed(5)
+    f1 = torch.randn(B, C, H, W, generator=g).to(dev()).to(dtype)
+    f2 = torch.randn(B, C, H, W, generator=g).to(dev()).to(dtype)
+    coords = torch.from_numpy(make_coords(B, H, W, W, 1, seed=9)[0]).to(dev())
+    cls = sb.CorrBlock1D if dtype == torch.float32 else sb.CorrBlockFast1D
+    big = cls(f1, f2)
+    assert big._state.pyr.buffer.numel() * big._state.pyr.buffer.element_size() > (96 << 20) or dtype == torch.float16
+    out_big = big(coords)
+    # same rows through the small-volume (4-window) path: one batch item, first 20 rows
+    small = cls(f1[:1, :, :20].contiguous(), f2[:1, :, :20].contiguous())
+    out_small = small(coords[:1, :, :20].contiguous())
+    assert torch.equal(out_big[:1, :, :20], out_small)
+    # and against the oracle for the fp32 case
+    if dtype == torch.float32:
+        lv = [l.squeeze(3)[:1, :20].cpu().numpy() for l in small.corr_pyramid]
+        want = oracle.c_lookup([np.ascontiguousarray(x) for x in lv],
+                               np.ascontiguousarray(coords[:1, :, :20].cpu().numpy()), 4)
+        assert rel_max(out_small.cpu().numpy(), want) < ORACLE_TOL
