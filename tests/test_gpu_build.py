@@ -131,3 +131,37 @@ def test_build_batch_independent_and_deterministic(sb):
     top = sb.CorrBlock1D(f1[:, :, :2].contiguous(), f2[:, :, :2].contiguous())._state.pyr
     for i in range(4):
         assert torch.equal(top.level(i), pyr.level(i)[:, :2])
+
+
+def test_middlebury_full_resolution_single_gpu(sb, oracle):
+    """BASELINE config 4: ~2000x3000 -> 500x750 at 1/4 res (W%4 != 0 -> padded staging, 6 M tiles x
+    3 N tiles, 2.2 GB pyramid, >2^31-byte offsets).  Checked through size-independent properties:
+    rows are independent (== a 2-row build of the same rows), pooling is exact, lookups on the big
+    pyramid (level-pair kernel) equal lookups on the 2-row pyramid (4-window kernel), and those
+    rows match the oracle."""
+    from gpu_util import dev, make_coords
+    B, C, H, W = 1, 256, 500, 750
+    g = torch.Generator(device="cpu").manual_seed(11)
+    f1 = torch.randn(B, C, H, W, generator=g).to(dev())
+    f2 = torch.randn(B, C, H, W, generator=g).to(dev())
+    blk = sb.CorrBlock1D(f1, f2)
+    pyr = blk._state.pyr
+    assert pyr.buffer.numel() * 4 > 2 ** 31
+    rows = [0, 249, 498]
+    for r0 in rows:
+        sub = sb.CorrBlock1D(f1[:, :, r0:r0 + 2].contiguous(), f2[:, :, r0:r0 + 2].contiguous())
+        for i in range(4):
+            assert torch.equal(sub._state.pyr.level(i), pyr.level(i)[:, r0:r0 + 2])
+    lv = [pyr.level(i)[:, 498:500] for i in range(4)]
+    for i in range(1, 4):
+        w = lv[i].shape[-1]
+        assert torch.equal(lv[i], (lv[i - 1][..., 0:2 * w:2] + lv[i - 1][..., 1:2 * w:2]) * 0.5)
+    want = oracle.c_pyramid(oracle.c_corr_volume(f1[:, :, 498:500].cpu().numpy().copy(),
+                                                 f2[:, :, 498:500].cpu().numpy().copy()), 4)
+    for i in range(4):
+        assert rel_max(lv[i].cpu().numpy(), want[i]) < VOL_TOL
+    coords = torch.from_numpy(make_coords(B, H, W, W, 1, seed=4)[0]).to(dev())
+    out = blk(coords)
+    assert tuple(out.shape) == (1, 36, 500, 750) and torch.isfinite(out).all()
+    sub = sb.CorrBlock1D(f1[:, :, 498:500].contiguous(), f2[:, :, 498:500].contiguous())
+    assert torch.equal(out[:, :, 498:500], sub(coords[:, :, 498:500].contiguous()))
