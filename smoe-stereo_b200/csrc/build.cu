@@ -404,19 +404,22 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 }
 
 // ---------------------------------------------------------------------- pitch-padding pre-pass
-// TMA needs 16-byte global strides; feature maps whose W*sizeof(T) is not a multiple of 16 are
-// copied once into a pitch-padded workspace (zero tail) and the tensor map points there.
+// TMA needs 16-byte global strides AND 16-byte-aligned box start addresses; feature maps whose
+// W*sizeof(T) is not a multiple of 16 are copied once into a pitch-padded workspace (zero tail)
+// and the tensor map points there.  (A flat (H*W,C,B) map over the unpadded tensor satisfies the
+// stride rule when H*W*sizeof(T) % 16 == 0 but faults on rows that start 8 bytes off -- tried.)
 template <typename T>
 __global__ void __launch_bounds__(256)
 pad_rows_kernel(const T* __restrict__ src, T* __restrict__ dst, long long rows, int W, int Wp) {
   pdl_launch_dependents();
   pdl_wait();
-  const long long total = rows * Wp;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / Wp;
-    const int w = static_cast<int>(i - r * Wp);
-    dst[i] = w < W ? src[r * W + w] : T(0);
+  // one warp per row: coalesced, no per-element division
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  for (long long r = warp0; r < rows; r += (long long)gridDim.x * 8) {
+    const T* s_ = src + r * W;
+    T* d_ = dst + r * Wp;
+    for (int w = lane; w < Wp; w += 32) d_[w] = w < W ? s_[w] : T(0);
   }
 }
 
@@ -581,8 +584,9 @@ int smoe_corr_build(const void* fmap1, const void* fmap2, int in_dtype, int B, i
     auto pad = [&](const void* src, int W, int Wp) -> const void* {
       void* dst = ws;
       const long long total = rows * Wp;
-      long long blocks = (total + 255) / 256;
-      if (blocks > 148ll * 16) blocks = 148ll * 16;
+      long long blocks = (rows + 7) / 8;
+      if (blocks > 148ll * 8) blocks = 148ll * 8;
+      (void)total;
       if (es == 4)
         launch_kernel(pad_rows_kernel<float>, dim3((unsigned)blocks), dim3(256), 0, st,
                       static_cast<const float*>(src), static_cast<float*>(dst), rows, W, Wp);

@@ -59,6 +59,7 @@ def test_build_vs_reference_golden(sb, name):
     (1, 256, 8, 312, 312),      # config 3 width (384x1248): 3 M tiles, 2 N tiles
     (1, 256, 3, 750, 750),      # config 4 width (W%4 != 0 -> padded staging), 6 M x 3 N tiles
     (1, 100, 2, 72, 520),       # C not a multiple of the K stage, W1 != W2, 3 N tiles
+    (2, 64, 4, 37, 52),         # padded staging for fmap1 only
 ])
 def test_build_shapes_vs_oracle(sb, oracle, shape):
     from gpu_util import dev
