@@ -27,17 +27,13 @@ constexpr int kFwdThreads = 128;  // 4 lanes per pixel
 // e[i] = lerp(v[i], v[i+1]) of the aligned chunks covering the pixel's window, plus the shift s
 // (window start inside the first chunk).  Output channel k of that level is e[s + k]: the
 // data-dependent shift is applied on the READ side, so the write side is one 16-byte store per
-// chunk.  Row stride WIN+4 words and an XOR of the chunk index with (p>>3)&3 keep both the
-// 16-byte writes and the shifted scalar reads (lane = pixel) nearly bank-conflict free.
+// chunk and the output loop is `LDS [row + s + k]` with immediate k.  Row stride WIN+4 words keeps
+// the 16-byte alignment and spreads rows over banks (the kernel is issue/latency-bound at
+// L2-resident sizes, so instruction count matters more than the residual 2-4 way conflicts:
+// 416 -> ~290 SASS instructions per thread, profiles/r01/README.md).
 template <int EPL> struct WinTile {
   static constexpr int kWin = 4 * EPL;
   static constexpr int kStride = kWin + 4;                 // words per (level,pixel) row
-  __device__ static __forceinline__ int chunk_word(int p, int chunk) {
-    return p * kStride + ((chunk ^ ((p >> 3) & 3)) << 2);
-  }
-  __device__ static __forceinline__ int elem_word(int p, int e) {
-    return chunk_word(p, e >> 2) + (e & 3);
-  }
 };
 
 template <typename VT, typename OT, int R, int NL, int TPX, bool STREAM>
@@ -47,6 +43,7 @@ lookup_fwd_vec_kernel(PyrDev pyr, const float* __restrict__ coords, long long co
   constexpr int EPL = Vec16<VT>::N;          // elements per 16-byte chunk
   constexpr int LOG_EPL = (EPL == 4) ? 2 : 3;
   constexpr int RD = 2 * R + 1;
+  constexpr int QMAX = (EPL - 1 + 2 * R + 1) >> LOG_EPL;   // last chunk a window can reach
   using Tile = WinTile<EPL>;
   static_assert(EPL - 1 + 2 * R + 2 <= 4 * EPL, "window must fit the 4 chunks of a lane group");
   __shared__ __align__(16) float s_win[NL][TPX * Tile::kStride];
@@ -74,14 +71,16 @@ lookup_fwd_vec_kernel(PyrDev pyr, const float* __restrict__ coords, long long co
     const int ci = (base >> LOG_EPL) + q;          // arithmetic shift == floor division
     if (q == 0) s_shift[l][p] = s;
     const int width = pyr.width[l];
-    const int nchunks = (width + EPL - 1) >> LOG_EPL;
-    const bool need = valid && (q * EPL < s + 2 * R + 2) && ci >= 0 && ci < nchunks;
+    const unsigned nchunks = (unsigned)(width + EPL - 1) >> LOG_EPL;
+    // chunk q intersects the window iff q*EPL <= s + 2R+1; one unsigned compare checks 0 <= ci < nchunks
+    const bool need = valid && (q < QMAX || (q == QMAX && s + 2 * R + 1 >= QMAX * EPL)) &&
+                      (unsigned)ci < nchunks;
 #pragma unroll
     for (int j = 0; j < EPL; ++j) v[l][j] = 0.f;
     if (need) {
       const VT* src = static_cast<const VT*>(pyr.ptr[l]) + row * pyr.pitch[l] + (long long)ci * EPL;
       Vec16<VT>::template load<STREAM>(src, v[l]);
-      if ((ci + 1) * EPL > width) {                // tail chunk: mask elements >= width
+      if (__builtin_expect((ci + 1) * EPL > width, 0)) {       // rare tail chunk: mask elements >= width
 #pragma unroll
         for (int j = 0; j < EPL; ++j)
           if (ci * EPL + j >= width) v[l][j] = 0.f;
@@ -89,6 +88,7 @@ lookup_fwd_vec_kernel(PyrDev pyr, const float* __restrict__ coords, long long co
     }
   }
   pdl_launch_dependents();   // all loads are in flight: let the successor's CTAs become resident
+  float* my_row = &s_win[0][p * Tile::kStride + q * EPL];
 #pragma unroll
   for (int l = 0; l < NL; ++l) {
     const float nxt = __shfl_down_sync(0xffffffffu, v[l][0], 1);   // first element of chunk q+1
@@ -99,7 +99,7 @@ lookup_fwd_vec_kernel(PyrDev pyr, const float* __restrict__ coords, long long co
       e[j] = to_float(lerp_ref<OT>(v[l][j], (j + 1 < EPL) ? v[l][j + 1] : nxt, dx));
 #pragma unroll
     for (int h = 0; h < EPL / 4; ++h)
-      *reinterpret_cast<float4*>(&s_win[l][Tile::chunk_word(p, q * (EPL / 4) + h)]) =
+      *reinterpret_cast<float4*>(my_row + l * (TPX * Tile::kStride) + 4 * h) =
           make_float4(e[4 * h], e[4 * h + 1], e[4 * h + 2], e[4 * h + 3]);
   }
   __syncthreads();
@@ -112,11 +112,9 @@ lookup_fwd_vec_kernel(PyrDev pyr, const float* __restrict__ coords, long long co
     const int pp = pg * 32 + lane;
     if (hw0 + pp < HW) {
       OT* dst = out + ((long long)b * (NL * RD) + l * RD) * HW + hw0 + pp;
-      const int sft = s_shift[l][pp];
-      const float* wrow = s_win[l];
+      const float* wrow = &s_win[l][pp * Tile::kStride] + s_shift[l][pp];
 #pragma unroll
-      for (int k = 0; k < RD; ++k)
-        dst[(long long)k * HW] = from_float<OT>(wrow[Tile::elem_word(pp, sft + k)]);
+      for (int k = 0; k < RD; ++k) dst[(long long)k * HW] = from_float<OT>(wrow[k]);
     }
   }
 }
