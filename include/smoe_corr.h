@@ -15,6 +15,7 @@
  *   smoe_corr_lookup           core/corr.py:127-146 (CorrBlock1D.__call__), core/corr.py:44-51
  *                              (CorrBlockFast1D.__call__), sampler/sampler.cpp:24-32 and
  *                              sampler/sampler_kernel.cu:19-60,107-136 (corr_sampler.forward)
+ *   smoe_corr_lookup_update    the loop glue of core/SMoEStereo.py:234-248 + the lookup (opt-in)
  *   smoe_corr_lookup_bwd       sampler/sampler.cpp:34-45, sampler/sampler_kernel.cu:63-105,138-166
  *                              (corr_sampler.backward)
  *   smoe_corr_fold_pyramid_grad  autograd of core/corr.py:122-125 (avg_pool2d backward chain)
@@ -131,6 +132,19 @@ int smoe_corr_build(const void* fmap1, const void* fmap2, int in_dtype, int B, i
 int smoe_corr_lookup(const smoe_pyramid_t* pyr, const float* coords, int64_t coords_batch_stride,
                      float coord_scale, int radius, void* out, int out_dtype,
                      smoe_stream_t stream);
+
+/*
+ * Lookup with the GRU loop's coordinate-update glue fused into the kernel prologue (opt-in
+ * extension).  Replaces, per iteration, the reference's elementwise launches
+ *   delta_flow[:,1] = 0; coords1 = coords1 + delta_flow        (core/SMoEStereo.py:245-248)
+ *   corr = corr_fn(coords1); flow = coords1 - coords0           (core/SMoEStereo.py:235-236)
+ * by ONE launch:  coords1_out = coords1 + (delta_flow.x, 0);  flow_out = coords1_out - coords0;
+ * out = lookup(coords1_out.x).  All coordinate tensors are contiguous (B,2,H,W1) fp32.
+ * delta_flow may be NULL (no update), flow_out may be NULL; coords1_out must not alias coords1.
+ */
+int smoe_corr_lookup_update(const smoe_pyramid_t* pyr, const float* coords1, const float* delta_flow,
+                            const float* coords0, float* coords1_out, float* flow_out, int radius,
+                            void* out, int out_dtype, smoe_stream_t stream);
 
 /*
  * Lookup backward (gradient w.r.t. the pyramid levels; coords get no gradient, core/corr.py:29).

@@ -24,7 +24,7 @@ SYMBOLS = (
     "smoe_corr_abi_version", "smoe_corr_last_error", "smoe_corr_device_supported",
     "smoe_corr_pyramid_layout", "smoe_corr_build_workspace_bytes", "smoe_corr_build",
     "smoe_corr_lookup", "smoe_corr_lookup_bwd", "smoe_corr_fold_pyramid_grad",
-    "smoe_corr_debug_set_timeline", "smoe_corr_build_bwd",
+    "smoe_corr_debug_set_timeline", "smoe_corr_build_bwd", "smoe_corr_lookup_update",
 )
 
 
@@ -61,6 +61,8 @@ def _declare(L: ctypes.CDLL) -> None:
                                   ctypes.c_uint, vp]
     L.smoe_corr_lookup.argtypes = [pp, vp, i64, f32, i32, vp, i32, vp]
     L.smoe_corr_lookup_bwd.argtypes = [pp, vp, i64, f32, i32, vp, i32, i32, vp]
+    L.smoe_corr_lookup_update.argtypes = [pp, vp, vp, vp, vp, vp, i32, vp, i32, vp]
+    L.smoe_corr_lookup_update.restype = i32
     L.smoe_corr_fold_pyramid_grad.argtypes = [pp, vp]
     L.smoe_corr_build_bwd.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, pp, f32, vp, vp, vp]
     L.smoe_corr_build_bwd.restype = i32

@@ -278,6 +278,49 @@ class _CorrBlockBase:
             return _LookupFn.apply(self._token, coords, self._state, out_dtype)
         return _lookup(p, coords, self.radius, out_dtype)
 
+    def lookup_update(self, coords1, delta_flow=None, coords0=None):
+        """Opt-in fused GRU-loop step.  Equivalent to the reference loop body
+        around the lookup (core/SMoEStereo.py:234-248):
+
+            delta_flow[:, 1] = 0; coords1 = coords1 + delta_flow      # skipped if delta_flow is None
+            corr = corr_fn(coords1); flow = coords1 - coords0          # flow None if coords0 is None
+
+        returns (corr, coords1_new, flow).  Without autograd this is ONE kernel launch instead of
+        four; when gradients are needed (training) it composes the differentiable pieces."""
+        p = self._state.pyr
+        out_dtype = torch.float32 if self._float_output else p.dtype
+        needs_grad = torch.is_grad_enabled() and (
+            self._token is not None or (delta_flow is not None and delta_flow.requires_grad)
+            or coords1.requires_grad)
+        if needs_grad:
+            if delta_flow is not None:
+                mask = delta_flow.new_tensor([1.0, 0.0]).view(1, 2, 1, 1)
+                coords1 = coords1 + delta_flow * mask
+            corr = self(coords1.detach())
+            flow = coords1 - coords0 if coords0 is not None else None
+            return corr, coords1, flow
+        for name, t in (("coords1", coords1), ("delta_flow", delta_flow), ("coords0", coords0)):
+            if t is None:
+                continue
+            _require_cuda(t, name)
+            if tuple(t.shape) != (p.B, 2, p.H, p.W1) or t.dtype != torch.float32:
+                raise RuntimeError(f"{name} must be a float32 tensor of shape ({p.B},2,{p.H},{p.W1})")
+        coords1 = coords1.contiguous()
+        delta_flow = delta_flow.contiguous() if delta_flow is not None else None
+        coords0 = coords0.contiguous() if coords0 is not None else None
+        c1_new = torch.empty_like(coords1)
+        flow = torch.empty_like(coords1) if coords0 is not None else None
+        out = torch.empty((p.B, p.num_levels * (2 * self.radius + 1), p.H, p.W1), dtype=out_dtype,
+                          device=p.device)
+        with _on_device(p.device):
+            rc = _lib.lib().smoe_corr_lookup_update(
+                p.ref, coords1.data_ptr(), delta_flow.data_ptr() if delta_flow is not None else None,
+                coords0.data_ptr() if coords0 is not None else None, c1_new.data_ptr(),
+                flow.data_ptr() if flow is not None else None, self.radius, out.data_ptr(),
+                _DTYPE_CODE[out_dtype], _stream_ptr(p.device))
+        _lib.check(rc, "smoe_corr_lookup_update")
+        return out, c1_new, flow
+
     @staticmethod
     def corr(fmap1, fmap2):
         """(B,D,H,W1),(B,D,H,W2) -> (B,H,W1,1,W2), same dtype (core/corr.py:148-156, :53-61).

@@ -139,6 +139,39 @@ template <typename T> __device__ __forceinline__ T from_float(float v);
 template <> __device__ __forceinline__ float from_float<float>(float v) { return v; }
 template <> __device__ __forceinline__ __half from_float<__half>(float v) { return __float2half_rn(v); }
 
+// Optional coordinate-update glue fused into the lookup prologue: the GRU
+// loop's  delta_flow[:,1] = 0; coords1 = coords1 + delta_flow; flow = coords1 - coords0
+// (core/SMoEStereo.py:236,245-248) -- three tiny elementwise launches per iteration in the
+// reference.  All tensors are contiguous (B,2,H,W1); `plane` = H*W1.  c1_out == nullptr: plain lookup.
+struct CoordUpd {
+  const float* delta;      // GRU update; only channel 0 (x) is applied.  May be nullptr.
+  const float* c0;         // coords0, needed iff flow_out != nullptr
+  float* c1_out;           // updated coordinates (must not alias the input coordinates)
+  float* flow_out;         // c1_out - coords0, or nullptr
+  long long plane;
+};
+
+// x coordinate of pixel (b, hw); in update mode one designated lane per pixel also writes the
+// updated coordinates / flow.
+__device__ __forceinline__ float fetch_coord(const float* __restrict__ coords, long long bstride,
+                                             const CoordUpd& u, int b, int hw, bool writer) {
+  float x = __ldg(coords + (long long)b * bstride + hw);
+  if (u.c1_out != nullptr) {
+    const long long o = (long long)b * 2 * u.plane + hw;
+    if (u.delta != nullptr) x += __ldg(u.delta + o);
+    if (writer) {
+      const float y = __ldg(coords + (long long)b * bstride + u.plane + hw);
+      u.c1_out[o] = x;
+      u.c1_out[o + u.plane] = y;
+      if (u.flow_out != nullptr) {
+        u.flow_out[o] = x - __ldg(u.c0 + o);
+        u.flow_out[o + u.plane] = y - __ldg(u.c0 + o + u.plane);
+      }
+    }
+  }
+  return x;
+}
+
 // Split a level coordinate into (base tap index, fractional weight).  Non-finite or
 // unrepresentably large coordinates are sent far out of range so that every tap is masked
 // (the reference's int cast of such values is undefined; all-zero is the defined behaviour here).

@@ -39,7 +39,7 @@ template <int EPL> struct WinTile {
 template <typename VT, typename OT, int R, int NL, int TPX, bool STREAM>
 __global__ void __launch_bounds__(4 * TPX)
 lookup_fwd_vec_kernel(PyrDev pyr, const float* __restrict__ coords, long long coords_bstride,
-                      float coord_scale, OT* __restrict__ out, int HW) {
+                      float coord_scale, OT* __restrict__ out, int HW, CoordUpd upd) {
   constexpr int EPL = Vec16<VT>::N;          // elements per 16-byte chunk
   constexpr int LOG_EPL = (EPL == 4) ? 2 : 3;
   constexpr int RD = 2 * R + 1;
@@ -56,7 +56,7 @@ lookup_fwd_vec_kernel(PyrDev pyr, const float* __restrict__ coords, long long co
   const int hw0 = blockIdx.x * TPX;
   const int hw = hw0 + p;
   const bool valid = hw < HW;
-  const float x0 = valid ? __ldg(coords + (long long)b * coords_bstride + hw) * coord_scale : 0.f;
+  const float x0 = valid ? fetch_coord(coords, coords_bstride, upd, b, hw, q == 0) * coord_scale : 0.f;
   const long long row = (long long)b * HW + hw;
 
   float v[NL][EPL];
@@ -131,7 +131,7 @@ lookup_fwd_vec_kernel(PyrDev pyr, const float* __restrict__ coords, long long co
 template <typename VT, typename OT, int R, int NP, int TPX, bool STREAM>
 __global__ void __launch_bounds__(8 * TPX)
 lookup_fwd_pair_kernel(PyrDev pyr, const float* __restrict__ coords, long long coords_bstride,
-                       float coord_scale, OT* __restrict__ out, int HW) {
+                       float coord_scale, OT* __restrict__ out, int HW, CoordUpd upd) {
   constexpr int EPL = Vec16<VT>::N;
   constexpr int LOG_EPL = (EPL == 4) ? 2 : 3;
   constexpr int RD = 2 * R + 1;
@@ -153,7 +153,7 @@ lookup_fwd_pair_kernel(PyrDev pyr, const float* __restrict__ coords, long long c
   const int hw0 = blockIdx.x * TPX;
   const int hw = hw0 + p;
   const bool valid = hw < HW;
-  const float x0 = valid ? __ldg(coords + (long long)b * coords_bstride + hw) * coord_scale : 0.f;
+  const float x0 = valid ? fetch_coord(coords, coords_bstride, upd, b, hw, q == 0) * coord_scale : 0.f;
   const long long row = (long long)b * HW + hw;
 
   float v[NP][EPL];
@@ -252,14 +252,14 @@ lookup_fwd_pair_kernel(PyrDev pyr, const float* __restrict__ coords, long long c
 template <typename VT, typename OT>
 __global__ void __launch_bounds__(128)
 lookup_fwd_generic_kernel(PyrDev pyr, const float* __restrict__ coords, long long coords_bstride,
-                          float coord_scale, int R, OT* __restrict__ out, int HW) {
+                          float coord_scale, int R, OT* __restrict__ out, int HW, CoordUpd upd) {
   pdl_launch_dependents();
   pdl_wait();
   const int hw = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
   if (hw >= HW) return;
   const int RD = 2 * R + 1;
-  const float x0 = __ldg(coords + (long long)b * coords_bstride + hw) * coord_scale;
+  const float x0 = fetch_coord(coords, coords_bstride, upd, b, hw, true) * coord_scale;
   const long long row = (long long)b * HW + hw;
   float lscale = 1.0f;
   for (int l = 0; l < pyr.num_levels; ++l) {
@@ -563,14 +563,14 @@ static bool volume_exceeds_l2(const PyrDev& d, long long rows, int elem_bytes) {
 
 template <typename VT, typename OT, int NL>
 static void launch_fwd_vec(const PyrDev& d, const float* coords, long long cbs, float cs, void* out,
-                           int HW, int B, cudaStream_t st) {
+                           int HW, int B, cudaStream_t st, const CoordUpd& upd) {
   int tile = pick_fwd_tile((long long)HW * B);
   if (tile != 64) tile = 32;
   dim3 grid((HW + tile - 1) / tile, B);
   const bool big = volume_exceeds_l2(d, (long long)HW * B, (int)sizeof(VT));
 #define SMOE_LAUNCH_FWD(TPX, STREAM)                                                               \
   launch_kernel(lookup_fwd_vec_kernel<VT, OT, 4, NL, TPX, STREAM>, grid, dim3(4 * TPX), 0, st, d,  \
-                coords, cbs, cs, static_cast<OT*>(out), HW)
+                coords, cbs, cs, static_cast<OT*>(out), HW, upd)
   if (tile == 64) {
     if (big) SMOE_LAUNCH_FWD(64, true); else SMOE_LAUNCH_FWD(64, false);
   } else {
@@ -584,35 +584,35 @@ static const bool g_force_pair = getenv("SMOE_CORR_FORCE_PAIR_LOOKUP") != nullpt
 
 template <typename VT, typename OT, int NP>
 static void launch_fwd_pair(const PyrDev& d, const float* coords, long long cbs, float cs, void* out,
-                            int HW, int B, cudaStream_t st) {
+                            int HW, int B, cudaStream_t st, const CoordUpd& upd) {
   constexpr int TPX = 32;
   dim3 grid((HW + TPX - 1) / TPX, B);
   const bool big = volume_exceeds_l2(d, (long long)HW * B, (int)sizeof(VT));
   if (big)
     launch_kernel(lookup_fwd_pair_kernel<VT, OT, 4, NP, TPX, true>, grid, dim3(8 * TPX), 0, st, d, coords,
-                  cbs, cs, static_cast<OT*>(out), HW);
+                  cbs, cs, static_cast<OT*>(out), HW, upd);
   else
     launch_kernel(lookup_fwd_pair_kernel<VT, OT, 4, NP, TPX, false>, grid, dim3(8 * TPX), 0, st, d, coords,
-                  cbs, cs, static_cast<OT*>(out), HW);
+                  cbs, cs, static_cast<OT*>(out), HW, upd);
 }
 
 template <typename VT, typename OT>
 static void dispatch_fwd_vec(int NL, const PyrDev& d, const float* coords, long long cbs, float cs,
-                             void* out, int HW, int B, cudaStream_t st) {
+                             void* out, int HW, int B, cudaStream_t st, const CoordUpd& upd) {
   // Volumes that stream from DRAM: two contiguous segments per pixel instead of four windows
   // (cfg3: 31.3 -> 26.8 us).  L2-resident volumes stay on the 4-lane kernel (3.65 vs 4.04 us at
   // cfg1: that regime is latency-bound and the pair kernel does more work per pixel).
   const bool pair = volume_exceeds_l2(d, (long long)HW * B, (int)sizeof(VT)) || g_force_pair;
   if (!g_no_pair && pair && (NL == 2 || NL == 4)) {
-    if (NL == 4) launch_fwd_pair<VT, OT, 2>(d, coords, cbs, cs, out, HW, B, st);
-    else launch_fwd_pair<VT, OT, 1>(d, coords, cbs, cs, out, HW, B, st);
+    if (NL == 4) launch_fwd_pair<VT, OT, 2>(d, coords, cbs, cs, out, HW, B, st, upd);
+    else launch_fwd_pair<VT, OT, 1>(d, coords, cbs, cs, out, HW, B, st, upd);
     return;
   }
   switch (NL) {
-    case 1: launch_fwd_vec<VT, OT, 1>(d, coords, cbs, cs, out, HW, B, st); break;
-    case 2: launch_fwd_vec<VT, OT, 2>(d, coords, cbs, cs, out, HW, B, st); break;
-    case 3: launch_fwd_vec<VT, OT, 3>(d, coords, cbs, cs, out, HW, B, st); break;
-    default: launch_fwd_vec<VT, OT, 4>(d, coords, cbs, cs, out, HW, B, st); break;
+    case 1: launch_fwd_vec<VT, OT, 1>(d, coords, cbs, cs, out, HW, B, st, upd); break;
+    case 2: launch_fwd_vec<VT, OT, 2>(d, coords, cbs, cs, out, HW, B, st, upd); break;
+    case 3: launch_fwd_vec<VT, OT, 3>(d, coords, cbs, cs, out, HW, B, st, upd); break;
+    default: launch_fwd_vec<VT, OT, 4>(d, coords, cbs, cs, out, HW, B, st, upd); break;
   }
 }
 
@@ -658,10 +658,12 @@ static int launch_bwd_dense(const smoe_pyramid_t* gp, const PyrDev& d, const flo
 
 extern "C" {
 
-int smoe_corr_lookup(const smoe_pyramid_t* pyr, const float* coords, int64_t coords_batch_stride,
-                     float coord_scale, int radius, void* out, int out_dtype,
-                     smoe_stream_t stream) {
-  using namespace smoe;
+}  // extern "C"
+
+namespace smoe {
+static int lookup_impl(const smoe_pyramid_t* pyr, const float* coords, int64_t coords_batch_stride,
+                       float coord_scale, int radius, void* out, int out_dtype, smoe_stream_t stream,
+                       const CoordUpd& upd) {
   if (int rc = validate_pyramid(pyr, "lookup")) return rc;
   SMOE_REQUIRE(radius >= 0 && radius <= 64, SMOE_ERR_INVALID_ARG, "lookup: radius %d outside [0,64]",
                radius);
@@ -680,26 +682,52 @@ int smoe_corr_lookup(const smoe_pyramid_t* pyr, const float* coords, int64_t coo
   if (radius == 4 && vec_ok(pyr)) {
     if (!f16v)
       dispatch_fwd_vec<float, float>(pyr->num_levels, d, coords, coords_batch_stride, coord_scale,
-                                     out, (int)HW, pyr->B, st);
+                                     out, (int)HW, pyr->B, st, upd);
     else if (f16o)
       dispatch_fwd_vec<__half, __half>(pyr->num_levels, d, coords, coords_batch_stride, coord_scale,
-                                       out, (int)HW, pyr->B, st);
+                                       out, (int)HW, pyr->B, st, upd);
     else
       dispatch_fwd_vec<__half, float>(pyr->num_levels, d, coords, coords_batch_stride, coord_scale,
-                                      out, (int)HW, pyr->B, st);
+                                      out, (int)HW, pyr->B, st, upd);
   } else {
     dim3 grid((unsigned)((HW + 127) / 128), pyr->B);
     if (!f16v)
       launch_kernel(lookup_fwd_generic_kernel<float, float>, grid, dim3(128), 0, st, d, coords,
-                    (long long)coords_batch_stride, coord_scale, radius, static_cast<float*>(out), (int)HW);
+                    (long long)coords_batch_stride, coord_scale, radius, static_cast<float*>(out), (int)HW, upd);
     else if (f16o)
       launch_kernel(lookup_fwd_generic_kernel<__half, __half>, grid, dim3(128), 0, st, d, coords,
-                    (long long)coords_batch_stride, coord_scale, radius, static_cast<__half*>(out), (int)HW);
+                    (long long)coords_batch_stride, coord_scale, radius, static_cast<__half*>(out), (int)HW, upd);
     else
       launch_kernel(lookup_fwd_generic_kernel<__half, float>, grid, dim3(128), 0, st, d, coords,
-                    (long long)coords_batch_stride, coord_scale, radius, static_cast<float*>(out), (int)HW);
+                    (long long)coords_batch_stride, coord_scale, radius, static_cast<float*>(out), (int)HW, upd);
   }
   return check_launch("lookup forward");
+}
+}  // namespace smoe
+
+extern "C" {
+
+int smoe_corr_lookup(const smoe_pyramid_t* pyr, const float* coords, int64_t coords_batch_stride,
+                     float coord_scale, int radius, void* out, int out_dtype,
+                     smoe_stream_t stream) {
+  const smoe::CoordUpd none = {nullptr, nullptr, nullptr, nullptr, 0};
+  return smoe::lookup_impl(pyr, coords, coords_batch_stride, coord_scale, radius, out, out_dtype, stream, none);
+}
+
+int smoe_corr_lookup_update(const smoe_pyramid_t* pyr, const float* coords1, const float* delta_flow,
+                            const float* coords0, float* coords1_out, float* flow_out, int radius,
+                            void* out, int out_dtype, smoe_stream_t stream) {
+  using namespace smoe;
+  if (int rc = validate_pyramid(pyr, "lookup_update")) return rc;
+  const long long plane = (long long)pyr->H * pyr->W1;
+  if (pyr->B == 0 || plane == 0) return SMOE_OK;
+  SMOE_REQUIRE(coords1 && coords1_out, SMOE_ERR_INVALID_ARG, "lookup_update: NULL coords1 / coords1_out");
+  SMOE_REQUIRE(coords1_out != coords1, SMOE_ERR_INVALID_ARG,
+               "lookup_update: coords1_out must not alias coords1 (several lanes read each coordinate)");
+  SMOE_REQUIRE(flow_out == nullptr || coords0 != nullptr, SMOE_ERR_INVALID_ARG,
+               "lookup_update: flow_out needs coords0");
+  const CoordUpd upd = {delta_flow, coords0, coords1_out, flow_out, plane};
+  return lookup_impl(pyr, coords1, 2 * plane, 1.0f, radius, out, out_dtype, stream, upd);
 }
 
 int smoe_corr_lookup_bwd(const smoe_pyramid_t* gp, const float* coords, int64_t coords_batch_stride,

@@ -151,3 +151,37 @@ def test_sharded_block_single_process_equals_full(sb):
         b = sb.CorrBlock1D(f1[:, :, lo:hi].contiguous(), f2[:, :, lo:hi].contiguous())
         parts.append(b(coords[:, :, lo:hi].contiguous()))
     assert torch.equal(torch.cat(parts, dim=2), full)
+
+
+@pytest.mark.parametrize("shape,levels,radius", [((2, 32, 6, 48), 4, 4), ((1, 32, 3, 37), 4, 4), ((1, 32, 4, 40), 3, 3)])
+def test_fused_lookup_update_equals_loop_glue(sb, shape, levels, radius):
+    """lookup_update == the reference loop body around the lookup (core/SMoEStereo.py:234-248),
+    bit for bit: coords1 + (dx, 0), lookup at the new x, flow = coords1 - coords0."""
+    from gpu_util import dev
+    B, C, H, W = shape
+    g = torch.Generator(device="cpu").manual_seed(W)
+    f1 = torch.randn(B, C, H, W, generator=g).to(dev())
+    f2 = torch.randn(B, C, H, W, generator=g).to(dev())
+    ys, xs = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+    coords0 = torch.stack([xs, ys], 0).float()[None].repeat(B, 1, 1, 1).to(dev())
+    coords1 = (coords0 - torch.rand(B, 2, H, W, generator=g).to(dev()) * 9).contiguous()
+    delta = torch.randn(B, 2, H, W, generator=g).to(dev())
+    blk = sb.CorrBlock1D(f1, f2, num_levels=levels, radius=radius)
+    with torch.no_grad():
+        d = delta.clone()
+        d[:, 1] = 0
+        want_c1 = coords1 + d
+        want_corr = blk(want_c1)
+        want_flow = want_c1 - coords0
+        corr, c1, flow = blk.lookup_update(coords1, delta, coords0)
+        assert torch.equal(c1, want_c1) and torch.equal(flow, want_flow) and torch.equal(corr, want_corr)
+        corr2, c2, flow2 = blk.lookup_update(coords1)            # no update, no flow
+        assert flow2 is None and torch.equal(c2, coords1) and torch.equal(corr2, blk(coords1))
+    # training: gradients reach delta_flow (x only) and the feature maps
+    f1g = f1.clone().requires_grad_(True)
+    dg = delta.clone().requires_grad_(True)
+    blk_g = sb.CorrBlock1D(f1g, f2, num_levels=levels, radius=radius)
+    corr, c1, flow = blk_g.lookup_update(coords1, dg, coords0)
+    (corr.sum() + (flow * 2.0).sum()).backward()
+    assert torch.all(dg.grad[:, 0] == 2.0) and torch.all(dg.grad[:, 1] == 0.0)
+    assert f1g.grad is not None and f1g.grad.abs().sum() > 0
