@@ -185,3 +185,31 @@ def test_fused_lookup_update_equals_loop_glue(sb, shape, levels, radius):
     (corr.sum() + (flow * 2.0).sum()).backward()
     assert torch.all(dg.grad[:, 0] == 2.0) and torch.all(dg.grad[:, 1] == 0.0)
     assert f1g.grad is not None and f1g.grad.abs().sum() > 0
+
+
+def test_second_device_and_threads_like_dataparallel(sb):
+    """nn.DataParallel drives the path from one host thread per GPU (train_stereo_sceneflow.py:133):
+    tensors on cuda:1 while cuda:0 is current, and concurrent calls from two threads."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import threading
+    torch.cuda.set_device(0)
+    g = torch.Generator(device="cpu").manual_seed(0)
+    f1 = torch.randn(1, 64, 4, 64, generator=g)
+    f2 = torch.randn(1, 64, 4, 64, generator=g)
+    coords = torch.zeros(1, 2, 4, 64)
+    coords[:, 0] = torch.arange(64).float() - 5.5
+    ref = sb.CorrBlock1D(f1.cuda(0), f2.cuda(0))(coords.cuda(0)).cpu()
+    out1 = sb.CorrBlock1D(f1.cuda(1), f2.cuda(1))(coords.cuda(1))      # current device is still 0
+    assert out1.device.index == 1 and torch.cuda.current_device() == 0
+    assert torch.equal(out1.cpu(), ref)
+    results = {}
+
+    def worker(d):
+        with torch.cuda.device(d):
+            for _ in range(20):
+                results[d] = sb.CorrBlock1D(f1.cuda(d), f2.cuda(d))(coords.cuda(d)).cpu()
+    th = [threading.Thread(target=worker, args=(d,)) for d in (0, 1)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert torch.equal(results[0], ref) and torch.equal(results[1], ref)
