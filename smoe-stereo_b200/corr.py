@@ -39,19 +39,30 @@ def _require_cuda(t: torch.Tensor, name: str) -> None:
         raise RuntimeError(f"{name} must be a CUDA tensor")
 
 
+# torch.cuda.current_stream() builds a Python Stream object (~6 us per call, half of an eager lookup's
+# host cost); the raw getters are what torch itself uses underneath.
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_raw_device = getattr(torch._C, "_cuda_getDevice", None) or torch.cuda.current_device
+
+
 def _stream_ptr(device: torch.device) -> ctypes.c_void_p:
+    if _raw_stream is not None:
+        idx = device.index if device.index is not None else _raw_device()
+        return ctypes.c_void_p(_raw_stream(idx))
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 class _on_device:
     """Make `device` current for the duration of a C-ABI call (no-op when it already is)."""
 
+    __slots__ = ("idx", "prev")
+
     def __init__(self, device: torch.device):
-        self.idx = device.index if device.index is not None else torch.cuda.current_device()
+        self.idx = device.index if device.index is not None else _raw_device()
         self.prev = None
 
     def __enter__(self):
-        cur = torch.cuda.current_device()
+        cur = _raw_device()
         if cur != self.idx:
             self.prev = cur
             torch.cuda.set_device(self.idx)
@@ -140,24 +151,33 @@ def _coords_plane(coords: torch.Tensor, B: int, H: int, W1: int):
     """Validate coords (B,>=1,H,W1) fp32 and return (tensor kept alive, batch stride in elements).
     Only channel 0 (x) is read (core/corr.py:129, :47)."""
     _require_cuda(coords, "coords")
-    if coords.dim() != 4 or coords.shape[0] != B or coords.shape[2] != H or coords.shape[3] != W1:
-        raise RuntimeError(f"coords must have shape ({B},>=1,{H},{W1}), got {tuple(coords.shape)}")
+    shp = coords.shape
+    if len(shp) != 4 or shp[0] != B or shp[2] != H or shp[3] != W1:
+        raise RuntimeError(f"coords must have shape ({B},>=1,{H},{W1}), got {tuple(shp)}")
     if coords.dtype != torch.float32:
         coords = coords.float()
-    if coords.stride(3) != 1 or coords.stride(2) != W1:
+    st = coords.stride()
+    if st[3] != 1 or st[2] != W1:
         coords = coords[:, :1].contiguous()
-    return coords, (coords.stride(0) if B > 1 else max(coords.stride(0), H * W1))
+        st = coords.stride()
+    return coords, (st[0] if B > 1 else max(st[0], H * W1))
+
+
+_lookup_fn = None
 
 
 def _lookup(pyr: FusedPyramid, coords: torch.Tensor, radius: int, out_dtype) -> torch.Tensor:
+    global _lookup_fn
+    if _lookup_fn is None:
+        _lookup_fn = _lib.lib().smoe_corr_lookup
     coords, bstride = _coords_plane(coords, pyr.B, pyr.H, pyr.W1)
     out = torch.empty((pyr.B, pyr.num_levels * (2 * radius + 1), pyr.H, pyr.W1), dtype=out_dtype,
                       device=pyr.device)
     with _on_device(pyr.device):
-        rc = _lib.lib().smoe_corr_lookup(pyr.ref, coords.data_ptr(), bstride, 1.0, radius,
-                                         out.data_ptr(), _DTYPE_CODE[out_dtype],
-                                         _stream_ptr(pyr.device))
-    _lib.check(rc, "smoe_corr_lookup")
+        rc = _lookup_fn(pyr.ref, coords.data_ptr(), bstride, 1.0, radius, out.data_ptr(),
+                        _DTYPE_CODE[out_dtype], _stream_ptr(pyr.device))
+    if rc:
+        _lib.check(rc, "smoe_corr_lookup")
     return out
 
 
