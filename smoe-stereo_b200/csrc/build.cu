@@ -208,7 +208,7 @@ template <typename IT, typename OT>
 __global__ void __launch_bounds__(kBuildThreads, 1)
 corr_build_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const __grid_constant__ OutMaps omaps, const int num_levels, const BuildDims dims,
-                  long long* __restrict__ timeline, const int dbg) {
+                  long long* __restrict__ timeline) {
   using Cfg = OperandCfg<IT>;
   constexpr int kSlabBytes = Cfg::kKT * 128;                 // one W slab x KT channels
   constexpr int kSlabsA = kBlockM / Cfg::kSlab;
@@ -368,19 +368,17 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             uint32_t acc[32];
             ptx::tmem_ld_32x32(taddr + c * kChunkCols + sub * 32, acc);
             ptx::tmem_ld_wait();
-            if (!(dbg & 4)) ChunkStage<OT>::run(acc, stg, lane, sub, sc, num_levels);
+            ChunkStage<OT>::run(acc, stg, lane, sub, sc, num_levels);
           }
         }
         ptx::fence_proxy_async_smem();             // generic-proxy smem writes -> async proxy (TMA)
         __syncwarp();
-        if (lane == 0 && m0 < dims.W1 && !(dbg & 1)) {
+        if (lane == 0 && m0 < dims.W1) {
           const int n0 = nt * dims.BN + c * kChunkCols;
           ptx::tma_store_3d(&omaps.lvl[0], stg + kStgL0, n0, m0, bh);
-          if (!(dbg & 2)) {
           if (num_levels > 1) ptx::tma_store_3d(&omaps.lvl[1], stg + kStgL1, n0 >> 1, m0, bh);
           if (num_levels > 2) ptx::tma_store_3d(&omaps.lvl[2], stg + kStgL2, n0 >> 2, m0, bh);
           if (num_levels > 3) ptx::tma_store_3d(&omaps.lvl[3], stg + kStgL3, n0 >> 3, m0, bh);
-          }
         }
         if (lane == 0) ptx::tma_store_commit();
         stg_sel = (stg_sel + 1) % kStgBufs;
@@ -496,7 +494,6 @@ static int make_level_tmap(CUtensorMap* out, const smoe_pyramid_t* pyr, int leve
 }
 
 static thread_local long long* g_timeline = nullptr;   // smoe_corr_debug_set_timeline
-static const int g_dbg = [] { const char* e = getenv("SMOE_CORR_DEBUG_FLAGS"); return e ? atoi(e) : 0; }();
 
 template <typename IT, typename OT>
 static int launch_build(const CUtensorMap& ta, const CUtensorMap& tb, const OutMaps& om, int num_levels,
@@ -510,7 +507,7 @@ static int launch_build(const CUtensorMap& ta, const CUtensorMap& tb, const OutM
   const long long items = (long long)dims.BH * dims.MT * dims.NT;
   const int grid = (int)(items < sms ? items : sms);
   SMOE_CUDA_OK(launch_kernel(kern, dim3(grid), dim3(kBuildThreads), kBuildSmemBytes, st, ta, tb, om,
-                             num_levels, dims, g_timeline, g_dbg));
+                             num_levels, dims, g_timeline));
   return check_launch("corr_build_kernel");
 }
 

@@ -94,9 +94,7 @@ lookup_fwd_vec_kernel(PyrDev pyr, const float* __restrict__ coords, long long co
     const float nxt = __shfl_down_sync(0xffffffffu, v[l][0], 1);   // first element of chunk q+1
     const float dx = dxs[l];
     float e[EPL];
-#pragma unroll
-    for (int j = 0; j < EPL; ++j)
-      e[j] = to_float(lerp_ref<OT>(v[l][j], (j + 1 < EPL) ? v[l][j + 1] : nxt, dx));
+    LerpChunk<OT, EPL>::run(v[l], nxt, dx, e);
 #pragma unroll
     for (int h = 0; h < EPL / 4; ++h)
       *reinterpret_cast<float4*>(my_row + l * (TPX * Tile::kStride) + 4 * h) =
@@ -209,12 +207,8 @@ lookup_fwd_pair_kernel(PyrDev pyr, const float* __restrict__ coords, long long c
     const float nxt_f = __shfl_down_sync(0xffffffffu, v[pr][0], 1);
     const float nxt_c = __shfl_down_sync(0xffffffffu, pc[0], 1);
     float ef[EPL], ec[EPL / 2];
-#pragma unroll
-    for (int j = 0; j < EPL; ++j)
-      ef[j] = to_float(lerp_ref<OT>(v[pr][j], (j + 1 < EPL) ? v[pr][j + 1] : nxt_f, dxf[pr]));
-#pragma unroll
-    for (int j = 0; j < EPL / 2; ++j)
-      ec[j] = to_float(lerp_ref<OT>(pc[j], (j + 1 < EPL / 2) ? pc[j + 1] : nxt_c, dxc[pr]));
+    LerpChunk<OT, EPL>::run(v[pr], nxt_f, dxf[pr], ef);
+    LerpChunk<OT, EPL / 2>::run(pc, nxt_c, dxc[pr], ec);
 #pragma unroll
     for (int h = 0; h < EPL / 4; ++h)
       *reinterpret_cast<float4*>(&s_fine[pr][p * FS + (q * (EPL / 4) + h) * 4]) =
