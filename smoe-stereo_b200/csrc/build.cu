@@ -165,37 +165,57 @@ template <> struct ChunkStage<float> {
 
 // fp16 pyramid: every level is rounded to half and the next level is pooled from the ROUNDED
 // values with an fp32 sum, which is what F.avg_pool2d does on a half tensor (core/corr.py:42).
-// 64 fp16 columns == 128 bytes, processed as two 32-column sub-chunks.
+// 64 fp16 columns == 128 bytes, processed as two 32-column sub-chunks.  Everything stays packed:
+// one F2FP per value pair, the power-of-two division as an exact HMUL2, pooling as
+// unpack -> fp32 (a+b)*0.5 -> pack (one rounding, like avg_pool2d's fp32 accumulator).
 template <> struct ChunkStage<__half> {
   static constexpr int kSubChunks = 2;
-  __device__ static float rh(float x) { return __half2float(__float2half_rn(x)); }
+  __device__ static __forceinline__ uint32_t as_u32(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+  template <int N>   // N pooled half2 outputs from 2N half2 inputs
+  __device__ static __forceinline__ void pool(const __half2* in, __half2* out) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      const float2 a = __half22float2(in[2 * j]), b = __half22float2(in[2 * j + 1]);
+      out[j] = __floats2half2_rn((a.x + a.y) * 0.5f, (b.x + b.y) * 0.5f);
+    }
+  }
   __device__ static void run(const uint32_t (&acc)[32], uint32_t stg, int row, int sub,
                              const Scaler& sc, int num_levels) {
-    float v[32];
     // the reference's einsum output is already fp16; the division then rounds a second time
-    sc.apply_rounded_half(acc, v);
+    __half2 h0[16];
+    if (sc.exact) {
+      const __half2 r2 = __float2half2_rn(sc.rcp);                 // power of two: exact
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        h0[j] = __hmul2_rn(__floats2half2_rn(__uint_as_float(acc[2 * j]), __uint_as_float(acc[2 * j + 1])), r2);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float2 f = __half22float2(
+            __floats2half2_rn(__uint_as_float(acc[2 * j]), __uint_as_float(acc[2 * j + 1])));
+        h0[j] = __floats2half2_rn(__fdiv_rn(f.x, sc.denom), __fdiv_rn(f.y, sc.denom));
+      }
+    }
 #pragma unroll
     for (int g = 0; g < 4; ++g)
-      st_shared_v4u(stg_addr(stg + kStgL0, 0, row, 64 * sub + 16 * g), pack_h2(v[8 * g], v[8 * g + 1]),
-                    pack_h2(v[8 * g + 2], v[8 * g + 3]), pack_h2(v[8 * g + 4], v[8 * g + 5]),
-                    pack_h2(v[8 * g + 6], v[8 * g + 7]));
+      st_shared_v4u(stg_addr(stg + kStgL0, 0, row, 64 * sub + 16 * g), as_u32(h0[4 * g]), as_u32(h0[4 * g + 1]),
+                    as_u32(h0[4 * g + 2]), as_u32(h0[4 * g + 3]));
     if (num_levels < 2) return;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = rh((v[2 * j] + v[2 * j + 1]) * 0.5f);
+    __half2 h1[8];
+    pool<8>(h0, h1);
 #pragma unroll
     for (int g = 0; g < 2; ++g)
-      st_shared_v4u(stg_addr(stg + kStgL1, 1, row, 32 * sub + 16 * g), pack_h2(v[8 * g], v[8 * g + 1]),
-                    pack_h2(v[8 * g + 2], v[8 * g + 3]), pack_h2(v[8 * g + 4], v[8 * g + 5]),
-                    pack_h2(v[8 * g + 6], v[8 * g + 7]));
+      st_shared_v4u(stg_addr(stg + kStgL1, 1, row, 32 * sub + 16 * g), as_u32(h1[4 * g]), as_u32(h1[4 * g + 1]),
+                    as_u32(h1[4 * g + 2]), as_u32(h1[4 * g + 3]));
     if (num_levels < 3) return;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = rh((v[2 * j] + v[2 * j + 1]) * 0.5f);
-    st_shared_v4u(stg_addr(stg + kStgL2, 2, row, 16 * sub), pack_h2(v[0], v[1]), pack_h2(v[2], v[3]),
-                  pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+    __half2 h2[4];
+    pool<4>(h1, h2);
+    st_shared_v4u(stg_addr(stg + kStgL2, 2, row, 16 * sub), as_u32(h2[0]), as_u32(h2[1]), as_u32(h2[2]),
+                  as_u32(h2[3]));
     if (num_levels < 4) return;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] = rh((v[2 * j] + v[2 * j + 1]) * 0.5f);
-    st_shared_v2u(stg_addr(stg + kStgL3, 3, row, 8 * sub), pack_h2(v[0], v[1]), pack_h2(v[2], v[3]));
+    __half2 h3[2];
+    pool<2>(h2, h3);
+    st_shared_v2u(stg_addr(stg + kStgL3, 3, row, 8 * sub), as_u32(h3[0]), as_u32(h3[1]));
   }
 };
 
