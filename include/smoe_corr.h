@@ -158,6 +158,23 @@ int smoe_corr_lookup_bwd(const smoe_pyramid_t* grad_pyr, const float* coords,
                          smoe_stream_t stream);
 
 /*
+ * Lookup backward for a whole step at once.  Autograd runs every lookup backward of a step before
+ * the build backward, so the num_iters lookups can be back-propagated together: per 32-pixel tile
+ * the gradient rows of all `num_levels` levels live in shared memory, the (coords[t], grad_out[t])
+ * tiles are streamed through, the levels are folded (avg_pool2d backward chain) and ONLY the folded
+ * level-0 gradient is written, once -- instead of num_iters read-modify-write passes over a
+ * gradient pyramid, a memset and a fold pass.  g0 describes that level-0 output (fp32; level_ptr[0],
+ * width[0] = W2, pitch[0]); accumulate != 0 adds to its current contents.  Result ==
+ * smoe_corr_lookup_bwd(ACCUMULATE) x num_iters followed by smoe_corr_fold_pyramid_grad.
+ * Host arrays of num_iters device pointers / strides.  Radius 4, H*W1*sizeof(grad) % 16 == 0 and
+ * 16-byte-aligned operands required (SMOE_ERR_UNSUPPORTED otherwise: use the per-call path).
+ */
+int smoe_corr_lookup_bwd_batched(const smoe_pyramid_t* g0, int num_levels, int num_iters,
+                                 const float* const* coords, const int64_t* coords_batch_stride,
+                                 const void* const* grad_out, int grad_out_dtype, int radius,
+                                 int accumulate, smoe_stream_t stream);
+
+/*
  * Fold the per-level gradients onto level 0 in place (avg_pool2d backward chain):
  *   g_{i-1}[., 2j] += g_i[., j]/2 ; g_{i-1}[., 2j+1] += g_i[., j]/2, for i = L-1 .. 1.
  */

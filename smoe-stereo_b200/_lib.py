@@ -18,6 +18,7 @@ OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_CUDA = 0, 1, 2, 3
 DTYPE_F32, DTYPE_F16 = 0, 1
 BUILD_TF32_TRUNCATE = 1
 BWD_OVERWRITE, BWD_ACCUMULATE = 0, 1
+MAX_BATCHED_ITERS = 48
 
 # every symbol include/smoe_corr.h declares
 SYMBOLS = (
@@ -25,6 +26,7 @@ SYMBOLS = (
     "smoe_corr_pyramid_layout", "smoe_corr_build_workspace_bytes", "smoe_corr_build",
     "smoe_corr_lookup", "smoe_corr_lookup_bwd", "smoe_corr_fold_pyramid_grad",
     "smoe_corr_debug_set_timeline", "smoe_corr_build_bwd", "smoe_corr_lookup_update",
+    "smoe_corr_lookup_bwd_batched",
 )
 
 
@@ -63,6 +65,8 @@ def _declare(L: ctypes.CDLL) -> None:
     L.smoe_corr_lookup_bwd.argtypes = [pp, vp, i64, f32, i32, vp, i32, i32, vp]
     L.smoe_corr_lookup_update.argtypes = [pp, vp, vp, vp, vp, vp, i32, vp, i32, vp]
     L.smoe_corr_lookup_update.restype = i32
+    L.smoe_corr_lookup_bwd_batched.argtypes = [pp, i32, i32, vp, vp, vp, i32, i32, i32, vp]
+    L.smoe_corr_lookup_bwd_batched.restype = i32
     L.smoe_corr_fold_pyramid_grad.argtypes = [pp, vp]
     L.smoe_corr_build_bwd.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, pp, f32, vp, vp, vp]
     L.smoe_corr_build_bwd.restype = i32

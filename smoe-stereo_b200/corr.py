@@ -147,6 +147,56 @@ def _build_backward(gp: FusedPyramid, fmap1: torch.Tensor, fmap2: torch.Tensor):
     return df1.to(fmap1.dtype), df2.to(fmap2.dtype)
 
 
+def _batched_smem_bytes(W2: int, num_levels: int, grad_elem: int) -> int:
+    off, w = 0, W2
+    for _ in range(num_levels):
+        off += (w + 3) // 4 * 4
+        w //= 2
+    return 32 * (off + 32) * 4 + 6 * (num_levels * 9 * (32 + 16 // grad_elem) * grad_elem + 32 * 4)
+
+
+def _batchable(pyr: FusedPyramid, coords: torch.Tensor, grad_out: torch.Tensor, radius: int):
+    """(coords, batch stride, grad_out) if this lookup's backward can join the batched kernel
+    (smoe_corr_lookup_bwd_batched), else None -> per-call accumulate path."""
+    if radius != 4 or grad_out.dtype not in _DTYPE_CODE:
+        return None
+    es = grad_out.element_size()
+    if (pyr.H * pyr.W1 * es) % 16 != 0 or _batched_smem_bytes(pyr.W2, pyr.num_levels, es) > 227 * 1024:
+        return None
+    grad_out = grad_out.contiguous()
+    coords, bstride = _coords_plane(coords, pyr.B, pyr.H, pyr.W1)
+    if coords.data_ptr() % 16 or grad_out.data_ptr() % 16 or bstride % 4:
+        return None
+    return coords, bstride, grad_out
+
+
+def _batched_lookup_backward(pyr: FusedPyramid, pending: list, radius: int, gp):
+    """Run the deferred lookup backwards of a step; returns a 1-level FusedPyramid holding the folded
+    level-0 gradient (adds to `gp`'s level 0 when some lookups took the per-call path)."""
+    accumulate = 1
+    if gp is None:
+        gp = FusedPyramid(pyr.B, pyr.H, pyr.W1, pyr.W2, 1, torch.float32, pyr.device)
+        accumulate = 0
+    L = _lib.lib()
+    by_dtype: dict = {}
+    for item in pending:
+        by_dtype.setdefault(item[2].dtype, []).append(item)
+    for dtype, items in by_dtype.items():
+        for i in range(0, len(items), _lib.MAX_BATCHED_ITERS):
+            chunk = items[i:i + _lib.MAX_BATCHED_ITERS]
+            n = len(chunk)
+            cptr = (ctypes.c_void_p * n)(*[c.data_ptr() for c, _, _ in chunk])
+            cstr = (ctypes.c_int64 * n)(*[s for _, s, _ in chunk])
+            gptr = (ctypes.c_void_p * n)(*[g.data_ptr() for _, _, g in chunk])
+            with _on_device(pyr.device):
+                rc = L.smoe_corr_lookup_bwd_batched(gp.ref, pyr.num_levels, n, cptr, cstr, gptr,
+                                                    _DTYPE_CODE[dtype], radius, accumulate,
+                                                    _stream_ptr(pyr.device))
+            _lib.check(rc, "smoe_corr_lookup_bwd_batched")
+            accumulate = 1
+    return gp
+
+
 def _coords_plane(coords: torch.Tensor, B: int, H: int, W1: int):
     """Validate coords (B,>=1,H,W1) fp32 and return (tensor kept alive, batch stride in elements).
     Only channel 0 (x) is read (core/corr.py:129, :47)."""
@@ -187,7 +237,8 @@ class _State:
 
     def __init__(self):
         self.pyr: FusedPyramid | None = None
-        self.grad_pyr: FusedPyramid | None = None
+        self.grad_pyr: FusedPyramid | None = None      # per-call (accumulating) backward path
+        self.pending: list = []                        # deferred lookup backwards (batched path)
         self.radius = 4
 
 
@@ -211,13 +262,16 @@ class _BuildFn(torch.autograd.Function):
     def backward(ctx, grad_token):
         fmap1, fmap2 = ctx.saved_tensors
         state = ctx.state
-        gp = state.grad_pyr
-        state.grad_pyr = None
-        if gp is None:
+        gp, pending = state.grad_pyr, state.pending
+        state.grad_pyr, state.pending = None, []
+        if gp is None and not pending:
             return torch.zeros_like(fmap1), torch.zeros_like(fmap2), None
-        with _on_device(gp.device):
-            rc = _lib.lib().smoe_corr_fold_pyramid_grad(gp.ref, _stream_ptr(gp.device))
-        _lib.check(rc, "smoe_corr_fold_pyramid_grad")
+        if gp is not None:          # lookups that went through the per-call accumulate path
+            with _on_device(gp.device):
+                rc = _lib.lib().smoe_corr_fold_pyramid_grad(gp.ref, _stream_ptr(gp.device))
+            _lib.check(rc, "smoe_corr_fold_pyramid_grad")
+        if pending:                 # all deferred lookups of the step in one pass (+ fold)
+            gp = _batched_lookup_backward(state.pyr, pending, state.radius, gp)
         df1, df2 = _build_backward(gp, fmap1, fmap2)
         return df1, df2, None
 
@@ -235,6 +289,10 @@ class _LookupFn(torch.autograd.Function):
         (coords,) = ctx.saved_tensors
         state = ctx.state
         pyr = state.pyr
+        item = _batchable(pyr, coords, grad_out, state.radius)
+        if item is not None:            # defer: the build backward handles the whole step at once
+            state.pending.append(item)
+            return torch.zeros(1, dtype=torch.float32, device=pyr.device), None, None, None
         if state.grad_pyr is None:      # zeroed once per backward pass, not once per call
             state.grad_pyr = FusedPyramid(pyr.B, pyr.H, pyr.W1, pyr.W2, pyr.num_levels,
                                           torch.float32, pyr.device, zero=True)

@@ -149,3 +149,71 @@ def test_native_build_backward_vs_oracle(sb, oracle, shape):
     e1, e2 = rel_max(df1.cpu().numpy(), want1), rel_max(df2.cpu().numpy(), want2)
     print(f"[build_bwd {shape}] rel_max d fmap1 {e1:.2e}, d fmap2 {e2:.2e}")
     assert e1 < E2E_GRAD_TOL and e2 < E2E_GRAD_TOL
+
+
+@pytest.mark.parametrize("shape,T,gdtype", [((2, 80, 184), 5, torch.float32), ((1, 135, 240), 3, torch.float32),
+                                            ((1, 6, 52), 50, torch.float32), ((2, 8, 40), 4, torch.float16)])
+def test_batched_backward_equals_accumulate_then_fold(sb, shape, T, gdtype):
+    """smoe_corr_lookup_bwd_batched (all iterations of a step in one pass, folded in shared memory)
+    == T x smoe_corr_lookup_bwd(ACCUMULATE) + smoe_corr_fold_pyramid_grad, bit for bit."""
+    from gpu_util import dev, make_coords
+    from smoe_stereo_b200 import _lib
+    from smoe_stereo_b200.corr import _batchable, _batched_lookup_backward, _stream_ptr
+    B, H, W = shape
+    gen = torch.Generator(device="cpu").manual_seed(T)
+    coords = [torch.from_numpy(make_coords(B, H, W, W, 1, seed=100 + t)[0]).to(dev()) for t in range(T)]
+    gouts = [torch.randn(B, 36, H, W, generator=gen).to(dev()).to(gdtype) for _ in range(T)]
+    pyr = sb.FusedPyramid(B, H, W, W, 4, torch.float32, dev())
+    # per-call path
+    gp = sb.FusedPyramid(B, H, W, W, 4, torch.float32, dev(), zero=True)
+    for c, g in zip(coords, gouts):
+        rc = _lib.lib().smoe_corr_lookup_bwd(gp.ref, c.data_ptr(), c.stride(0), 1.0, 4, g.data_ptr(),
+                                             _lib.DTYPE_F16 if gdtype == torch.float16 else _lib.DTYPE_F32,
+                                             _lib.BWD_ACCUMULATE, _stream_ptr(dev()))
+        _lib.check(rc, "bwd")
+    _lib.check(_lib.lib().smoe_corr_fold_pyramid_grad(gp.ref, _stream_ptr(dev())), "fold")
+    # batched path (T = 50 exercises the chunking at 48 iterations and the accumulate flag)
+    items = [_batchable(pyr, c, g, 4) for c, g in zip(coords, gouts)]
+    assert all(it is not None for it in items)
+    g0 = _batched_lookup_backward(pyr, items, 4, None)
+    assert g0.num_levels == 1
+    a, b = g0.level(0), gp.level(0)
+    if T <= 48:
+        assert torch.equal(a, b)
+    else:                       # two chunks are folded separately: same math, different rounding
+        assert rel_max(a.cpu().numpy(), b.cpu().numpy()) < 1e-6
+
+
+def test_batched_and_per_call_paths_mix(sb):
+    """A step whose lookups are partly batchable (radius 4 ...) and partly not still sums correctly:
+    force the mix by marking every other lookup non-batchable."""
+    from gpu_util import dev, make_coords
+    import smoe_stereo_b200.corr as corr_mod
+    B, C, H, W = 1, 32, 4, 48
+    g = torch.Generator(device="cpu").manual_seed(0)
+    f1 = torch.randn(B, C, H, W, generator=g).to(dev())
+    f2 = torch.randn(B, C, H, W, generator=g).to(dev())
+    coords = [torch.from_numpy(make_coords(B, H, W, W, 1, seed=t)[0]).to(dev()) for t in range(4)]
+    gouts = [torch.randn(B, 36, H, W, generator=g).to(dev()) for _ in range(4)]
+
+    def run(flaky):
+        a = f1.clone().requires_grad_(True)
+        b = f2.clone().requires_grad_(True)
+        blk = sb.CorrBlock1D(a, b)
+        loss = sum((blk(c) * go).sum() for c, go in zip(coords, gouts))
+        orig = corr_mod._batchable
+        calls = {"n": 0}
+
+        def sometimes(*args):
+            calls["n"] += 1
+            return None if (flaky and calls["n"] % 2) else orig(*args)
+        corr_mod._batchable = sometimes
+        try:
+            loss.backward()
+        finally:
+            corr_mod._batchable = orig
+        return a.grad, b.grad
+    ga, gb = run(False)
+    ma, mb = run(True)
+    assert rel_max(ma.cpu().numpy(), ga.cpu().numpy()) < 1e-5
+    assert rel_max(mb.cpu().numpy(), gb.cpu().numpy()) < 1e-5

@@ -73,7 +73,17 @@ report("zero gradient pyramid", timeit(graph_of(lambda: gp.buffer.zero_())[0]), 
 report(f"{iters} x lookup backward (accumulate)", timeit(graph_of(lambda: [bwd(t) for t in range(iters)])[0]), iters * px * 468)
 report("fold pyramid gradient", timeit(graph_of(fold)[0]), px * (2 * widths[0] + sum(widths[1:])) * 4)
 report("build backward (2 GEMMs)", timeit(graph_of(lambda: _build_backward(gp, f1, f2))[0]), px * widths[0] * 4 + 4 * B * C * H * W * 4)
+from smoe_stereo_b200.corr import _batchable, _batched_lookup_backward
+items = [_batchable(pyr, coords[t], gouts[t], r) for t in range(iters)]
+g0holder = {}
+def batched():
+    g0holder["g"] = _batched_lookup_backward(pyr, items, r, None)
+    return g0holder["g"]
+t_batched = timeit(graph_of(batched)[0])
+print(f"{'-> batched backward (all iters + fold)':34s} {t_batched:9.1f} us   replaces zero + {iters} x backward + fold = "
+      f"{rows[2][1] + rows[3][1] + rows[4][1]:.1f} us")
 tot = sum(r_[1] for r_ in rows)
+print(f"{'sum with batched backward':34s} {rows[0][1] + rows[1][1] + t_batched + rows[5][1]:9.1f} us")
 print(f"{'sum':34s} {tot:9.1f} us")
 # reference-style dense backward for comparison: zeros_like + scatter per level per iteration
 vol = pyr.level(0).contiguous()
