@@ -152,7 +152,7 @@ def _batched_smem_bytes(W2: int, num_levels: int, grad_elem: int) -> int:
     for _ in range(num_levels):
         off += (w + 3) // 4 * 4
         w //= 2
-    return 32 * (off + 32) * 4 + 6 * (num_levels * 9 * (32 + 16 // grad_elem) * grad_elem + 32 * 4)
+    return 32 * (off + 32) * 4 + 4 * (num_levels * 9 * (32 + 32 // grad_elem) * grad_elem + 32 * 4)
 
 
 def _batchable(pyr: FusedPyramid, coords: torch.Tensor, grad_out: torch.Tensor, radius: int):

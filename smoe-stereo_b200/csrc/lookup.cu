@@ -470,7 +470,7 @@ lookup_bwd_dense_kernel(PyrDev gp, const float* __restrict__ coords, long long c
 // fold kernel) the DRAM traffic drops from ~T*97 MB + 2*166 MB to T*17 MB + 87 MB at config 2.
 // The arithmetic per element is the same as accumulate + fold (same order), fp32, radius 4.
 constexpr int kMaxBatchedIters = 48;
-constexpr int kBatchedStages = 6;
+constexpr int kBatchedStages = 4;
 struct BwdBatch {
   const float* coords[kMaxBatchedIters];
   const void* gout[kMaxBatchedIters];
@@ -493,10 +493,13 @@ template <int N> __device__ __forceinline__ void cp_async_wait() {
 }
 
 // elements per grad-tile row: a 16-byte multiple (cp.async) that is not a multiple of 32 words
-template <typename GT> struct BatchedTile { static constexpr int kStride = kTilePx + 16 / (int)sizeof(GT); };
+// elements per grad-tile row: 40 words for fp32 puts the 4 levels of a pixel (9 rows apart) 8 banks apart
+// and the 8 pixels of a warp in between: conflict-free tile reads; fp16 rows only need 16-byte alignment
+template <typename GT> struct BatchedTile { static constexpr int kStride = kTilePx + 32 / (int)sizeof(GT); };
+constexpr int kBatchedThreads = 256;   // two threads per (pixel, level): taps 0-4 and 5-9
 
 template <typename GT, int NL>
-__global__ void __launch_bounds__(kFwdThreads)
+__global__ void __launch_bounds__(kBatchedThreads)
 lookup_bwd_batched_kernel(const __grid_constant__ BwdBatch batch, const BatchedGeom geo,
                           float* __restrict__ g0_out, long long g0_pitch, int HW, int accumulate) {
   constexpr int R = 4, RD = 9;
@@ -520,7 +523,7 @@ lookup_bwd_batched_kernel(const __grid_constant__ BwdBatch batch, const BatchedG
     constexpr int kPiecesPerRow = kTilePx * (int)sizeof(GT) / 16;
     constexpr int kElemsPerPiece = 16 / (int)sizeof(GT);
     const GT* g = static_cast<const GT*>(batch.gout[t]) + (long long)b * NC * HW + hw0;
-    for (int i = tid; i < NC * kPiecesPerRow; i += kFwdThreads) {
+    for (int i = tid; i < NC * kPiecesPerRow; i += kBatchedThreads) {
       const int c = i / kPiecesPerRow, e0 = (i - c * kPiecesPerRow) * kElemsPerPiece;
       const int bytes = max(0, min(16, (npx - e0) * (int)sizeof(GT)));
       const GT* src = g + (long long)c * HW + (bytes > 0 ? e0 : 0);
@@ -539,47 +542,64 @@ lookup_bwd_batched_kernel(const __grid_constant__ BwdBatch batch, const BatchedG
     if (t < batch.T) issue(t, t); else cp_async_commit();     // exactly one group per slot
   }
   // rows start from zero (or from the existing level-0 gradient when accumulating)
-  for (int i = tid; i < kTilePx * geo.rowlen / 4; i += kFwdThreads)
+  for (int i = tid; i < kTilePx * geo.rowlen / 4; i += kBatchedThreads)
     reinterpret_cast<float4*>(s_rows)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (accumulate) {
     __syncthreads();
     for (int pp = 0; pp < npx; ++pp)
-      for (int j = tid; j < geo.width[0]; j += kFwdThreads)
+      for (int j = tid; j < geo.width[0]; j += kBatchedThreads)
         s_rows[pp * geo.rowlen + j] = g0_out[((long long)b * HW + hw0 + pp) * g0_pitch + j];
   }
 
   // one thread per (pixel, level): its 2r+2 taps are contiguous in the shared-memory row, so there
   // is no 16-byte chunking (that only matters for global memory) and no idle slot
-  const int p = tid >> 2, l = tid & 3;
+  const int p = (tid >> 2) & (kTilePx - 1), l = tid & 3, half = tid >> 7;   // half: taps 0-4 / 5-9
   const bool active = p < npx && l < NL;
   float* rowl = s_rows + p * geo.rowlen + geo.off[l];
   const int width = geo.width[l];
   const float lscale = 1.0f / (float)(1 << l);
   for (int t = 0; t < batch.T; ++t) {
     const int buf = t % kBatchedStages;
-    cp_async_wait<kBatchedStages - 1>();
-    __syncthreads();                       // tile t visible to everyone (and row init on t == 0)
+    // groups committed so far: kBatchedStages + (t-1) (the refill of this iteration comes after the
+    // wait), so at most kBatchedStages-2 may still be pending for tile t to have landed
+    cp_async_wait<kBatchedStages - 2>();
+    __syncthreads();                       // tile t visible to everyone; everyone finished tile t-1
+    // refill the buffer consumed in the PREVIOUS iteration (one barrier per iteration suffices)
+    if (t >= 1) {
+      if (t - 1 + kBatchedStages < batch.T) issue(t - 1 + kBatchedStages, (t - 1) % kBatchedStages);
+      else cp_async_commit();
+    }
     if (active) {
       const GT* tl = reinterpret_cast<const GT*>(s_tiles + buf * kTileBytes) + (l * RD) * kBatchedTileStride + p;
       int base;
       float dx;
       split_coord(s_x[buf * kTilePx + p] * lscale, R, base, dx);
-      float gm1 = 0.f;
+      // this thread's 5 taps: all shared-memory loads first, then the math, then the stores, so
+      // the read-modify-writes do not serialise on the shared-memory latency
+      const int t0 = half * 5;
+      float cur[5], g[6];
+      bool ok[5];
+      g[0] = half ? to_float(tl[(t0 - 1) * kBatchedTileStride]) : 0.f;
 #pragma unroll
-      for (int tt = 0; tt <= RD; ++tt) {
-        const float g0 = (tt < RD) ? to_float(tl[tt * kBatchedTileStride]) : 0.f;
-        const int idx = base + tt;
-        if ((unsigned)idx < (unsigned)width) rowl[idx] += BwdTap<float>::eval(gm1, g0, tt > 0, tt < RD, dx);
-        gm1 = g0;
+      for (int k = 0; k < 5; ++k) {
+        g[k + 1] = (t0 + k < RD) ? to_float(tl[(t0 + k) * kBatchedTileStride]) : 0.f;
+        const int idx = base + t0 + k;
+        ok[k] = (unsigned)idx < (unsigned)width;
+        cur[k] = ok[k] ? rowl[idx] : 0.f;
       }
+#pragma unroll
+      for (int k = 0; k < 5; ++k)
+        cur[k] += BwdTap<float>::eval(g[k], g[k + 1], t0 + k > 0, t0 + k < RD, dx);
+#pragma unroll
+      for (int k = 0; k < 5; ++k)
+        if (ok[k]) rowl[base + t0 + k] = cur[k];
     }
-    __syncthreads();                       // everyone is done with buffer `buf`
-    if (t + kBatchedStages < batch.T) issue(t + kBatchedStages, buf); else cp_async_commit();
   }
+  __syncthreads();                         // all scatters done before the fold reads the rows
   // fold the levels in shared memory and write level 0 (same chain as fold_grad_*_kernel);
   // which coarser levels cover column j depends on j only, so it is resolved once per column
   const int w0 = geo.width[0];
-  for (int j = tid; j < w0; j += kFwdThreads) {
+  for (int j = tid; j < w0; j += kBatchedThreads) {
     int top = 0;
     for (int lv = 1; lv < NL; ++lv) {
       if ((j >> lv) >= geo.width[lv]) break;
@@ -976,7 +996,7 @@ int smoe_corr_lookup_bwd_batched(const smoe_pyramid_t* g0, int num_levels, int n
   // made every scatter an 8-way bank conflict: 810 us instead of ~200 us at config 2.)
   geo.rowlen = off + ((4 - off % 32) + 32) % 32;
   const size_t smem = (size_t)kTilePx * geo.rowlen * 4 +
-                      kBatchedStages * ((size_t)num_levels * 9 * (kTilePx + 16 / ges) * ges + kTilePx * 4);
+                      kBatchedStages * ((size_t)num_levels * 9 * (kTilePx + 32 / ges) * ges + kTilePx * 4);
   // (the Python side bounds this with off + 32 words per row)
   SMOE_REQUIRE(smem <= 227 * 1024, SMOE_ERR_UNSUPPORTED,
                "lookup_bwd_batched: W2=%d needs %zu bytes of shared memory per CTA", g0->width[0], smem);
@@ -987,7 +1007,7 @@ int smoe_corr_lookup_bwd_batched(const smoe_pyramid_t* g0, int num_levels, int n
   do {                                                                                                   \
     SMOE_CUDA_OK(cudaFuncSetAttribute(lookup_bwd_batched_kernel<GT, NLV>,                                \
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
-    SMOE_CUDA_OK(launch_kernel(lookup_bwd_batched_kernel<GT, NLV>, grid, dim3(kFwdThreads), smem, st,     \
+    SMOE_CUDA_OK(launch_kernel(lookup_bwd_batched_kernel<GT, NLV>, grid, dim3(kBatchedThreads), smem, st, \
                                batch, geo, out, (long long)g0->pitch[0], (int)HW, accumulate));           \
   } while (0)
   const bool f16g = grad_out_dtype == SMOE_DTYPE_F16;
