@@ -106,9 +106,11 @@ int64_t smoe_corr_build_workspace_bytes(int B, int C, int H, int W1, int W2, int
  *   level(i+1)[., j]     = (level i[., 2j] + level i[., 2j+1]) / 2,  j < floor(W2_i/2)
  * computed on tcgen05 tensor cores (kind::tf32 for fp32 inputs, kind::f16 for fp16 inputs,
  * fp32 accumulation in TMEM), operands staged by TMA, scale and pooling fused in the epilogue.
- * pyr->dtype is the output type (fp32, or fp16 when the inputs are fp16 -- the reference's
- * reg_cuda path under autocast; each fp16 level is pooled from the rounded previous level, as
- * F.avg_pool2d on a half tensor does).  The division is a true fp32 division as in
+ * pyr->dtype is the output type: fp32, or fp16.  fp16 inputs + fp16 pyramid is the reference's
+ * reg_cuda path under autocast (each fp16 level is pooled from the rounded previous level, as
+ * F.avg_pool2d on a half tensor does).  fp32 inputs + fp16 pyramid is an opt-in storage format
+ * (one rounding of the fp32 result, ~5e-4 relative): half the pyramid bytes, so e.g. the B=8
+ * training volume fits in L2.  The division is a true fp32 division as in
  * core/corr.py:156 (for fp16 outputs it is applied to the fp16-rounded sum, as the reference's
  * fp16 einsum output is).
  */

@@ -21,6 +21,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 
 import torch
 
@@ -31,6 +32,22 @@ __all__ = ["CorrBlock1D", "CorrBlockFast1D", "PytorchAlternateCorrBlock1D", "Cor
            "AlternateCorrBlock"]
 
 _DTYPE_CODE = {torch.float32: _lib.DTYPE_F32, torch.float16: _lib.DTYPE_F16}
+
+# Opt-in storage format of the volume/pyramid for fp32 feature maps in CorrBlock1D / the "alt"
+# alias: None = fp32 (the reference's "reg" semantics, default); torch.float16 = round the fp32
+# tensor-core result once to fp16 (~5e-4 relative, inside north_star's 1e-3), halving the pyramid
+# so that e.g. the B=8 training volume (166 MB) becomes L2-resident.  Lookup outputs stay fp32.
+# Also settable with SMOE_CORR_VOLUME_DTYPE=fp16 in the environment.
+_default_volume_dtype = torch.float16 if os.environ.get("SMOE_CORR_VOLUME_DTYPE", "").lower() in (
+    "fp16", "float16", "half") else None
+
+
+def set_default_volume_dtype(dtype) -> None:
+    """None / torch.float32 -> fp32 pyramids (default); torch.float16 -> fp16 storage (see above)."""
+    global _default_volume_dtype
+    if dtype not in (None, torch.float32, torch.float16):
+        raise ValueError("volume dtype must be None, torch.float32 or torch.float16")
+    _default_volume_dtype = None if dtype in (None, torch.float32) else dtype
 
 
 # ------------------------------------------------------------------------------------ helpers
@@ -333,14 +350,17 @@ class _CorrBlockBase:
         fmap1 = fmap1.contiguous()
         fmap2 = fmap2.contiguous()
         st = _State()
-        st.num_levels, st.radius, st.pyr_dtype = num_levels, radius, fmap1.dtype
+        pyr_dtype = fmap1.dtype
+        if self._float_output and fmap1.dtype == torch.float32 and _default_volume_dtype is not None:
+            pyr_dtype = _default_volume_dtype
+        st.num_levels, st.radius, st.pyr_dtype = num_levels, radius, pyr_dtype
         self._state = st
         self._token = None
         if torch.is_grad_enabled() and (fmap1.requires_grad or fmap2.requires_grad):
             self._token = _BuildFn.apply(fmap1, fmap2, st)
         else:
             st.pyr = FusedPyramid(fmap1.shape[0], fmap1.shape[2], fmap1.shape[3], fmap2.shape[3],
-                                  num_levels, fmap1.dtype, fmap1.device)
+                                  num_levels, pyr_dtype, fmap1.device)
             _build_into(st.pyr, fmap1, fmap2)
 
     @property

@@ -137,6 +137,7 @@ template <typename OT> struct ChunkStage;
 
 template <> struct ChunkStage<float> {
   static constexpr int kSubChunks = 1;     // 32 fp32 columns == 128 bytes
+  template <bool>
   __device__ static void run(const uint32_t (&acc)[32], uint32_t stg, int row, int /*sub*/,
                              const Scaler& sc, int num_levels) {
     float v[32];
@@ -179,11 +180,21 @@ template <> struct ChunkStage<__half> {
       out[j] = __floats2half2_rn((a.x + a.y) * 0.5f, (b.x + b.y) * 0.5f);
     }
   }
+  // kEinsumIsHalf: fp16 feature maps -- the reference's einsum output is already fp16 and the
+  // division rounds a second time (reg_cuda path).  Otherwise (fp32 feature maps, fp16 STORAGE
+  // opted into by the caller) the fp32 quotient is rounded once.
+  template <bool kEinsumIsHalf>
   __device__ static void run(const uint32_t (&acc)[32], uint32_t stg, int row, int sub,
                              const Scaler& sc, int num_levels) {
-    // the reference's einsum output is already fp16; the division then rounds a second time
     __half2 h0[16];
-    if (sc.exact) {
+    if (!kEinsumIsHalf) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float a = __uint_as_float(acc[2 * j]), b = __uint_as_float(acc[2 * j + 1]);
+        h0[j] = sc.exact ? __floats2half2_rn(a * sc.rcp, b * sc.rcp)
+                         : __floats2half2_rn(__fdiv_rn(a, sc.denom), __fdiv_rn(b, sc.denom));
+      }
+    } else if (sc.exact) {
       const __half2 r2 = __float2half2_rn(sc.rcp);                 // power of two: exact
 #pragma unroll
       for (int j = 0; j < 16; ++j)
@@ -388,7 +399,7 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             uint32_t acc[32];
             ptx::tmem_ld_32x32(taddr + c * kChunkCols + sub * 32, acc);
             ptx::tmem_ld_wait();
-            ChunkStage<OT>::run(acc, stg, lane, sub, sc, num_levels);
+            ChunkStage<OT>::template run<sizeof(IT) == 2>(acc, stg, lane, sub, sc, num_levels);
           }
         }
         ptx::fence_proxy_async_smem();             // generic-proxy smem writes -> async proxy (TMA)
@@ -565,8 +576,6 @@ int smoe_corr_build(const void* fmap1, const void* fmap2, int in_dtype, int B, i
   for (int i = 1; i < pyr->num_levels; ++i)
     SMOE_REQUIRE(pyr->width[i] == pyr->width[i - 1] / 2, SMOE_ERR_INVALID_ARG,
                  "build: level %d width %d is not floor(%d/2)", i, pyr->width[i], pyr->width[i - 1]);
-  SMOE_REQUIRE(!(in_dtype == SMOE_DTYPE_F32 && pyr->dtype == SMOE_DTYPE_F16), SMOE_ERR_UNSUPPORTED,
-               "build: fp16 pyramid from fp32 feature maps is not part of the reference API");
   if (B == 0 || H == 0 || W1 == 0 || W2 == 0) return SMOE_OK;
   SMOE_REQUIRE(fmap1 && fmap2, SMOE_ERR_INVALID_ARG, "build: NULL feature map pointer");
   SMOE_REQUIRE(aligned16(fmap1) && aligned16(fmap2), SMOE_ERR_INVALID_ARG,
@@ -644,6 +653,8 @@ int smoe_corr_build(const void* fmap1, const void* fmap2, int in_dtype, int B, i
   OutMaps om;
   for (int i = 0; i < SMOE_MAX_LEVELS; ++i)
     if (int rc = make_level_tmap(&om.lvl[i], pyr, i < levels ? i : 0)) return rc;
+  if (in_dtype == SMOE_DTYPE_F32 && pyr->dtype == SMOE_DTYPE_F16)      // opt-in fp16 storage
+    return launch_build<float, __half>(ta, tb, om, levels, dims, st);
   if (in_dtype == SMOE_DTYPE_F32) return launch_build<float, float>(ta, tb, om, levels, dims, st);
   if (pyr->dtype == SMOE_DTYPE_F16) return launch_build<__half, __half>(ta, tb, om, levels, dims, st);
   return launch_build<__half, float>(ta, tb, om, levels, dims, st);

@@ -213,3 +213,36 @@ def test_second_device_and_threads_like_dataparallel(sb):
     [t.start() for t in th]
     [t.join() for t in th]
     assert torch.equal(results[0], ref) and torch.equal(results[1], ref)
+
+
+def test_optin_fp16_volume_storage(sb, oracle):
+    """set_default_volume_dtype(float16): fp32 feature maps, tensor-core result rounded once to fp16
+    for storage (opt-in).  Still inside north_star's 1e-3; lookups stay fp32; training works."""
+    from gpu_util import dev, make_coords
+    B, C, H, W = 1, 256, 8, 240
+    rs = np.random.RandomState(3)
+    f1 = rs.standard_normal((B, C, H, W)).astype(np.float32)
+    f2 = rs.standard_normal((B, C, H, W)).astype(np.float32)
+    want_lv = oracle.c_pyramid(oracle.c_corr_volume(f1, f2), 4)
+    coords = make_coords(B, H, W, W, 1, seed=1)[0]
+    want = oracle.c_lookup(want_lv, np.ascontiguousarray(coords), 4)
+    sb.set_default_volume_dtype(torch.float16)
+    try:
+        t1 = torch.from_numpy(f1).to(dev()).requires_grad_(True)
+        t2 = torch.from_numpy(f2).to(dev())
+        blk = sb.CorrBlock1D(t1, t2)
+        assert blk._state.pyr.dtype == torch.float16
+        for i, lv in enumerate(blk.corr_pyramid):
+            assert rel_max(lv.squeeze(3).float().detach().cpu().numpy(), want_lv[i]) < 1e-3
+        out = blk(torch.from_numpy(coords).to(dev()))
+        assert out.dtype == torch.float32
+        e = rel_max(out.detach().cpu().numpy(), want)
+        print(f"[fp16 storage] lookup rel_max {e:.2e}")
+        assert e < 1e-3
+        out.square().sum().backward()
+        assert torch.isfinite(t1.grad).all() and t1.grad.abs().sum() > 0
+        # the fast block keeps the reference rule (volume dtype == feature dtype)
+        assert sb.CorrBlockFast1D(t1.detach(), t2)._state.pyr.dtype == torch.float32
+    finally:
+        sb.set_default_volume_dtype(None)
+    assert sb.CorrBlock1D(t1.detach(), t2)._state.pyr.dtype == torch.float32

@@ -23,7 +23,8 @@ for t in range(iters):
     c[:, 0] = xs - torch.rand(B, H, 1, generator=g) * 48 - torch.randn(B, H, W, generator=g) * (0.5 * t)
     coords.append(c.to(dev))
 gouts = [torch.randn(B, 36, H, W, generator=g).to(dev) for _ in range(iters)]
-pyr = sb.FusedPyramid(B, H, W, W, L, torch.float32, dev)
+VOL = torch.float16 if os.environ.get("SMOE_CORR_VOLUME_DTYPE") else torch.float32
+pyr = sb.FusedPyramid(B, H, W, W, L, VOL, dev)
 gp = sb.FusedPyramid(B, H, W, W, L, torch.float32, dev, zero=True)
 peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"] \
     if os.path.exists(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")) else 6549.4
