@@ -16,10 +16,12 @@ ncu --set full --clock-control none --import-source on -k regex:corr_build_kerne
 echo "build cfg1 rc=$?"
 PROBE="python tools/lookup_probe.py cfg3"
 $PROBE > /dev/null 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:lookup_fwd_vec -s 40 -c 2 -o $OUT/lookup_cfg3 $PROBE > $OUT/ncu_lookup3.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:lookup_fwd_pair -s 40 -c 2 -o $OUT/lookup_cfg3 $PROBE > $OUT/ncu_lookup3.log 2>&1
 echo "lookup cfg3 rc=$?"
 TRAIN="python tools/train_step_probe.py"
-$TRAIN > $OUT/train_plain.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:"lookup_bwd_acc|fold_grad|corr_build_bwd|corr_build_kernel" -s 4 -c 6 -o $OUT/train_cfg2 $TRAIN > $OUT/ncu_train.log 2>&1
-echo "train cfg2 rc=$?"
-ls -la $OUT
+$TRAIN > $OUT/train_plain.log 2>&1 || exit 1
+for k in lookup_bwd_batched lookup_bwd_acc fold_grad corr_build_bwd lookup_bwd_dense; do
+  ncu --set full --clock-control none --import-source on -k regex:$k -s 2 -c 1 -o $OUT/train_$k $TRAIN > $OUT/ncu_train_$k.log 2>&1
+  echo "$k rc=$?"
+done
+ls -la $OUT | head -30
