@@ -816,10 +816,6 @@ static int launch_bwd_dense(const smoe_pyramid_t* gp, const PyrDev& d, const flo
 
 }  // namespace smoe
 
-extern "C" {
-
-}  // extern "C"
-
 namespace smoe {
 static int lookup_impl(const smoe_pyramid_t* pyr, const float* coords, int64_t coords_batch_stride,
                        float coord_scale, int radius, void* out, int out_dtype, smoe_stream_t stream,
