@@ -22,6 +22,7 @@ FLAGS = [
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC",
     *(["-Xptxas", "-v"] if os.environ.get("SMOE_PTXAS_V") else []),
+    *os.environ.get("SMOE_NVCC_DEFS", "").split(),      # experiment switches (-DNAME=VALUE ...)
 ]
 
 

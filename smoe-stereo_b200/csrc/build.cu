@@ -32,20 +32,33 @@ namespace smoe {
 // ------------------------------------------------------------------------------ tile constants
 constexpr int kBlockM = 128;          // UMMA M (TMEM lanes)
 constexpr int kBlockN = 256;          // max UMMA N / accumulator columns per buffer
-constexpr int kStages = 4;
+// Probe build (SMOE_NVCC_DEFS=-DSMOE_BUILD_PROBES python smoe-stereo_b200/build.py --force): the
+// environment variable SMOE_CORR_BUILD_DEBUG then switches off parts of the kernel (1: operand
+// loads, 2: result stores, 4: MMAs) to time the rest alone.  Results are garbage; never shipped.
+#ifdef SMOE_BUILD_PROBES
+constexpr bool kProbes = true;
+#else
+constexpr bool kProbes = false;
+#endif
+constexpr int kMaxStages = 8;              // ring depth is chosen per launch (BuildDims::stages)
+constexpr int kEpiWarps = 4;                // one per TMEM lane quadrant
 constexpr int kStageABytes = 16 * 1024;   // 128 rows x KT channels
-constexpr int kStageBBytes = 32 * 1024;   // 256 cols x KT channels
-constexpr int kStageBytes = kStageABytes + kStageBBytes;
-constexpr int kBuildThreads = 192;
+constexpr int kStageBBytes = 32 * 1024;   // 256 cols x KT channels at most; a launch whose N tiles
+                                          // are narrower packs its stages tighter (stage_bytes)
+constexpr int kMaxSmemBytes = 226 * 1024; // dynamic shared memory budget (227 KiB opt-in limit on
+                                          // sm_100 minus the kernel's static barriers)
+constexpr int kBuildThreads = 64 + 32 * kEpiWarps;
 constexpr int kTmemCols = 512;
-// epilogue staging: per warp 2 buffers x (32 rows x (128+64+32+16) bytes) for levels 0..3
-// (buffer padded to 8 KiB so that every level-0 tile stays 1 KiB aligned: the swizzle is a
-// function of the shared-memory address)
-constexpr int kStgL0 = 0, kStgL1 = 4096, kStgL2 = 6144, kStgL3 = 7168, kStgBytes = 8192;
-constexpr int kStgBufs = 1;                        // staging buffers per epilogue warp
-constexpr int kStgPerWarp = kStgBufs * kStgBytes;
-constexpr size_t kBuildSmemBytes =
-    (size_t)kStages * kStageBytes + 4 * kStgPerWarp + 1024;   // + alignment slack
+// epilogue staging: per warp one 4 KiB tile per pyramid level (32 rows x up to 128 bytes).
+// Level 0 leaves as one 128-byte-wide box per chunk.  A coarser level i only produces 128>>i bytes
+// per row and chunk; rows that narrow are expensive to store (a 16-byte row is half a DRAM
+// sector: every level-3 row cost a read-modify-write, and TMA cost is per row, not per byte --
+// profiles/r01/README.md), so the chunks of a level are gathered over up to 2^i chunks and leave
+// as one wider box (see GroupPlan).
+constexpr int kStgLevelBytes = 4096;
+constexpr int kStgBytes = SMOE_MAX_LEVELS * kStgLevelBytes;
+constexpr int kStgPerWarp = kStgBytes;
+constexpr int kBuildSmemFixed = kEpiWarps * kStgPerWarp + 1024;      // staging + alignment slack
 
 template <typename T> struct OperandCfg;
 template <> struct OperandCfg<float> {
@@ -72,6 +85,9 @@ struct BuildDims {
   float denom;               // level0 = sum / denom   (core/corr.py:156: corr / sqrt(D))
   float rcp;                 // 1/denom, used when it is exact (denom a power of two)
   int rcp_exact;
+  int stages;                // operand ring: depth and bytes per stage (A 16 KiB + the B slabs
+  int stage_bytes;           // one N tile needs), sized to fill shared memory
+  int debug;                 // probe builds only (kProbes)
 };
 
 // Division exactly as the reference performs it: a true fp32 division, replaced by the (bit-
@@ -106,14 +122,36 @@ struct Scaler {
 };
 
 // ------------------------------------------------------------------------------------ epilogue
-// Staging tile of level i for one warp: 32 rows x (128 >> i) bytes, dense, with the TMA swizzle of
-// that row width (128B / 64B / 32B / none) applied to the 16-byte chunk index so that the 32
-// lanes (one row each) write without bank conflicts.  tile bases are 1 KiB / 512 B / 256 B aligned.
-__device__ __forceinline__ uint32_t stg_addr(uint32_t tile, int level, int row, int byte_off) {
-  const uint32_t lin = (uint32_t)row * (128u >> level) + (uint32_t)byte_off;
-  const uint32_t mask = level == 0 ? 7u : (level == 1 ? 3u : (level == 2 ? 1u : 0u));
+// Staging tile of width class d for one warp: 32 rows x (128 >> d) bytes, dense, with the TMA
+// swizzle of that row width (128B / 64B / 32B / none) applied to the 16-byte chunk index so that
+// the 32 lanes (one row each) write without bank conflicts.
+__device__ __forceinline__ uint32_t stg_addr(uint32_t tile, int d, int row, int byte_off) {
+  const uint32_t lin = (uint32_t)row * (128u >> d) + (uint32_t)byte_off;
+  const uint32_t mask = (8u >> d) - 1u;
   return tile + (lin ^ (((lin >> 7) & mask) << 4));
 }
+// Where chunk c of a tile with `chunks` chunks puts its level-i output.  Chunks are gathered into
+// aligned power-of-two groups of at most 2^i chunks that lie inside the tile (buddy
+// decomposition: 5 chunks at level 3 -> groups of 4 + 1); a group of 2^k chunks is stored as one
+// box of width class d = i - k (row = 128 >> d bytes) once its last chunk has been staged.
+struct GroupPlan {
+  int d[SMOE_MAX_LEVELS];       // width class of the group's staging tile / tensor map
+  int off[SMOE_MAX_LEVELS];     // byte offset of this chunk inside a staged row
+  int first[SMOE_MAX_LEVELS];   // first chunk of the group
+  bool flush[SMOE_MAX_LEVELS];  // this chunk completes the group
+  __device__ __forceinline__ GroupPlan(int c, int chunks) {
+#pragma unroll
+    for (int i = 0; i < SMOE_MAX_LEVELS; ++i) {
+      int k = i;
+      while (k > 0 && ((c >> k) << k) + (1 << k) > chunks) --k;
+      const int s = (c >> k) << k;
+      d[i] = i - k;
+      first[i] = s;
+      off[i] = (c - s) * (128 >> i);
+      flush[i] = (c - s) == (1 << k) - 1;
+    }
+  }
+};
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, float a, float b, float c, float d) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
                : "memory");
@@ -139,28 +177,30 @@ template <> struct ChunkStage<float> {
   static constexpr int kSubChunks = 1;     // 32 fp32 columns == 128 bytes
   template <bool>
   __device__ static void run(const uint32_t (&acc)[32], uint32_t stg, int row, int /*sub*/,
-                             const Scaler& sc, int num_levels) {
+                             const Scaler& sc, int num_levels, const GroupPlan& gp) {
     float v[32];
     sc.apply(acc, v);
 #pragma unroll
     for (int g = 0; g < 8; ++g)
-      st_shared_v4(stg_addr(stg + kStgL0, 0, row, 16 * g), v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+      st_shared_v4(stg_addr(stg, 0, row, 16 * g), v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
     if (num_levels < 2) return;
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = (v[2 * j] + v[2 * j + 1]) * 0.5f;
 #pragma unroll
     for (int g = 0; g < 4; ++g)
-      st_shared_v4(stg_addr(stg + kStgL1, 1, row, 16 * g), v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+      st_shared_v4(stg_addr(stg + kStgLevelBytes, gp.d[1], row, gp.off[1] + 16 * g), v[4 * g], v[4 * g + 1],
+                   v[4 * g + 2], v[4 * g + 3]);
     if (num_levels < 3) return;
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = (v[2 * j] + v[2 * j + 1]) * 0.5f;
 #pragma unroll
     for (int g = 0; g < 2; ++g)
-      st_shared_v4(stg_addr(stg + kStgL2, 2, row, 16 * g), v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+      st_shared_v4(stg_addr(stg + 2 * kStgLevelBytes, gp.d[2], row, gp.off[2] + 16 * g), v[4 * g],
+                   v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
     if (num_levels < 4) return;
 #pragma unroll
     for (int j = 0; j < 4; ++j) v[j] = (v[2 * j] + v[2 * j + 1]) * 0.5f;
-    st_shared_v4(stg_addr(stg + kStgL3, 3, row, 0), v[0], v[1], v[2], v[3]);
+    st_shared_v4(stg_addr(stg + 3 * kStgLevelBytes, gp.d[3], row, gp.off[3]), v[0], v[1], v[2], v[3]);
   }
 };
 
@@ -185,7 +225,7 @@ template <> struct ChunkStage<__half> {
   // opted into by the caller) the fp32 quotient is rounded once.
   template <bool kEinsumIsHalf>
   __device__ static void run(const uint32_t (&acc)[32], uint32_t stg, int row, int sub,
-                             const Scaler& sc, int num_levels) {
+                             const Scaler& sc, int num_levels, const GroupPlan& gp) {
     __half2 h0[16];
     if (!kEinsumIsHalf) {
 #pragma unroll
@@ -209,29 +249,32 @@ template <> struct ChunkStage<__half> {
     }
 #pragma unroll
     for (int g = 0; g < 4; ++g)
-      st_shared_v4u(stg_addr(stg + kStgL0, 0, row, 64 * sub + 16 * g), as_u32(h0[4 * g]), as_u32(h0[4 * g + 1]),
+      st_shared_v4u(stg_addr(stg, 0, row, 64 * sub + 16 * g), as_u32(h0[4 * g]), as_u32(h0[4 * g + 1]),
                     as_u32(h0[4 * g + 2]), as_u32(h0[4 * g + 3]));
     if (num_levels < 2) return;
     __half2 h1[8];
     pool<8>(h0, h1);
 #pragma unroll
     for (int g = 0; g < 2; ++g)
-      st_shared_v4u(stg_addr(stg + kStgL1, 1, row, 32 * sub + 16 * g), as_u32(h1[4 * g]), as_u32(h1[4 * g + 1]),
+      st_shared_v4u(stg_addr(stg + kStgLevelBytes, gp.d[1], row, gp.off[1] + 32 * sub + 16 * g), as_u32(h1[4 * g]), as_u32(h1[4 * g + 1]),
                     as_u32(h1[4 * g + 2]), as_u32(h1[4 * g + 3]));
     if (num_levels < 3) return;
     __half2 h2[4];
     pool<4>(h1, h2);
-    st_shared_v4u(stg_addr(stg + kStgL2, 2, row, 16 * sub), as_u32(h2[0]), as_u32(h2[1]), as_u32(h2[2]),
+    st_shared_v4u(stg_addr(stg + 2 * kStgLevelBytes, gp.d[2], row, gp.off[2] + 16 * sub), as_u32(h2[0]), as_u32(h2[1]), as_u32(h2[2]),
                   as_u32(h2[3]));
     if (num_levels < 4) return;
     __half2 h3[2];
     pool<2>(h2, h3);
-    st_shared_v2u(stg_addr(stg + kStgL3, 3, row, 8 * sub), as_u32(h3[0]), as_u32(h3[1]));
+    st_shared_v2u(stg_addr(stg + 3 * kStgLevelBytes, gp.d[3], row, gp.off[3] + 8 * sub), as_u32(h3[0]), as_u32(h3[1]));
   }
 };
 
 struct OutMaps {
-  CUtensorMap lvl[SMOE_MAX_LEVELS];   // 3-D (W2_i, W1, B*H) maps of the pyramid levels
+  // 3-D (W2_i, W1, B*H) maps of pyramid level i with a box of width class d (128 >> d bytes x 32
+  // rows), d <= i: index i*(i+1)/2 + d
+  CUtensorMap m[SMOE_MAX_LEVELS * (SMOE_MAX_LEVELS + 1) / 2];
+  __host__ __device__ static constexpr int index(int level, int d) { return level * (level + 1) / 2 + d; }
 };
 
 // -------------------------------------------------------------------------------------- kernel
@@ -249,7 +292,7 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   static_assert((kBlockN / Cfg::kSlab) * kSlabBytes == kStageBBytes, "B stage size");
 
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t s_full[kStages], s_empty[kStages], s_tfull[2], s_tempty[2];
+  __shared__ __align__(8) uint64_t s_full[kMaxStages], s_empty[kMaxStages], s_tfull[2], s_tempty[2];
   __shared__ uint32_t s_tmem_base;
 
   // debug timeline (smoe_corr_debug_set_timeline): clock64 stamps, 16 slots per role per CTA
@@ -266,14 +309,14 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmap_a);
     ptx::prefetch_tensormap(&tmap_b);
-    for (int i = 0; i < num_levels; ++i) ptx::prefetch_tensormap(&omaps.lvl[i]);
-    for (int i = 0; i < kStages; ++i) {
+    for (int i = 0; i < OutMaps::index(num_levels, 0); ++i) ptx::prefetch_tensormap(&omaps.m[i]);
+    for (int i = 0; i < dims.stages; ++i) {
       ptx::mbar_init(ptx::smem_u32(&s_full[i]), 1);
       ptx::mbar_init(ptx::smem_u32(&s_empty[i]), 1);
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(ptx::smem_u32(&s_tfull[i]), 1);
-      ptx::mbar_init(ptx::smem_u32(&s_tempty[i]), 128);
+      ptx::mbar_init(ptx::smem_u32(&s_tempty[i]), 32 * kEpiWarps);
     }
     ptx::fence_barrier_init();
   }
@@ -308,8 +351,13 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         for (int ks = 0; ks < num_k; ++ks) {
           ptx::mbar_wait(ptx::smem_u32(&s_empty[stage]), phase ^ 1u);
           const uint32_t full = ptx::smem_u32(&s_full[stage]);
+          if (kProbes && (dims.debug & 1)) {
+            ptx::mbar_arrive(full);
+            if (++stage == dims.stages) { stage = 0; phase ^= 1u; }
+            continue;
+          }
           ptx::mbar_expect_tx(full, tx_bytes);
-          const uint32_t sa = smem_base + stage * kStageBytes;
+          const uint32_t sa = smem_base + stage * dims.stage_bytes;
           const uint32_t sb = sa + kStageABytes;
 #pragma unroll
           for (int j = 0; j < kSlabsA; ++j)
@@ -318,7 +366,7 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           for (int j = 0; j < slabs_b; ++j)
             ptx::tma_load_4d(sb + j * kSlabBytes, &tmap_b, full, nt * dims.BN + j * Cfg::kSlab, h,
                              ks * Cfg::kKT, b);
-          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          if (++stage == dims.stages) { stage = 0; phase ^= 1u; }
         }
         stamp(0, 1 + it);                 // all loads of item `it` issued
       }
@@ -344,10 +392,11 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           ptx::tc_fence_after_sync();
           if (ks == 0) stamp(1, 3 * it);            // first stage of the item landed
           if (ks == num_k - 1) stamp(1, 3 * it + 1);  // last stage landed
-          const uint32_t sa = smem_base + stage * kStageBytes;
+          const uint32_t sa = smem_base + stage * dims.stage_bytes;
           const uint32_t sb = sa + kStageABytes;
 #pragma unroll
           for (int kk = 0; kk < kKSteps; ++kk) {
+            if (kProbes && (dims.debug & 4)) break;
             const uint64_t adesc =
                 ptx::make_smem_desc(sa + kk * kKStepBytes, kSlabBytes, Cfg::kSBO, Cfg::kLayout);
             const uint64_t bdesc =
@@ -358,7 +407,7 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
               ptx::mma_f16(d_tmem, adesc, bdesc, idesc, (ks | kk) != 0 ? 1u : 0u);
           }
           ptx::tc_commit(ptx::smem_u32(&s_empty[stage]));     // smem slot free when MMAs retire
-          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          if (++stage == dims.stages) { stage = 0; phase ^= 1u; }
         }
         ptx::tc_commit(ptx::smem_u32(&s_tfull[buf]));          // accumulator ready
         stamp(1, 3 * it + 2);
@@ -372,10 +421,11 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     constexpr int kChunkCols = 32 * kSub;
     const int quad = warp & 3;                    // TMEM lane quadrant this warp may read
     const Scaler sc{dims.denom, dims.rcp, dims.rcp_exact};
-    const uint32_t stg_base = smem_base + kStages * kStageBytes + (uint32_t)(warp - 2) * kStgPerWarp;
+    // staging tiles are 1 KiB aligned (smem_base is, stages and tiles are KiB multiples): the
+    // swizzle XOR in stg_addr then equals the TMA's function of the absolute address
+    const uint32_t stg_base = smem_base + dims.stages * dims.stage_bytes + (uint32_t)(warp - 2) * kStgPerWarp;
     int buf = 0;
     uint32_t bphase = 0;
-    int stg_sel = 0;
     int it = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
       const int nt = item % dims.NT;
@@ -389,9 +439,9 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)buf * kBlockN;
       const int chunks = (n_valid + kChunkCols - 1) / kChunkCols;
       for (int c = 0; c < chunks; ++c) {
-        const uint32_t stg = stg_base + (uint32_t)stg_sel * kStgBytes;
-        // the TMA stores that last read this staging buffer (two chunks ago) must have drained
-        if (lane == 0) ptx::tma_store_wait_read<kStgBufs - 1>();
+        const GroupPlan gp(c, chunks);
+        // the TMA stores that last read the staging tiles must have drained
+        if (lane == 0) ptx::tma_store_wait_read<0>();
         __syncwarp();
 #pragma unroll
         for (int sub = 0; sub < kSub; ++sub) {
@@ -399,20 +449,20 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             uint32_t acc[32];
             ptx::tmem_ld_32x32(taddr + c * kChunkCols + sub * 32, acc);
             ptx::tmem_ld_wait();
-            ChunkStage<OT>::template run<sizeof(IT) == 2>(acc, stg, lane, sub, sc, num_levels);
+            ChunkStage<OT>::template run<sizeof(IT) == 2>(acc, stg_base, lane, sub, sc, num_levels, gp);
           }
         }
         ptx::fence_proxy_async_smem();             // generic-proxy smem writes -> async proxy (TMA)
         __syncwarp();
-        if (lane == 0 && m0 < dims.W1) {
-          const int n0 = nt * dims.BN + c * kChunkCols;
-          ptx::tma_store_3d(&omaps.lvl[0], stg + kStgL0, n0, m0, bh);
-          if (num_levels > 1) ptx::tma_store_3d(&omaps.lvl[1], stg + kStgL1, n0 >> 1, m0, bh);
-          if (num_levels > 2) ptx::tma_store_3d(&omaps.lvl[2], stg + kStgL2, n0 >> 2, m0, bh);
-          if (num_levels > 3) ptx::tma_store_3d(&omaps.lvl[3], stg + kStgL3, n0 >> 3, m0, bh);
+        if (lane == 0 && m0 < dims.W1 && !(kProbes && (dims.debug & 2))) {
+          const int n0 = nt * dims.BN;
+#pragma unroll
+          for (int i = 0; i < SMOE_MAX_LEVELS; ++i)
+            if (i < num_levels && gp.flush[i])
+              ptx::tma_store_3d(&omaps.m[OutMaps::index(i, gp.d[i])], stg_base + i * kStgLevelBytes,
+                                (n0 + gp.first[i] * kChunkCols) >> i, m0, bh);
         }
         if (lane == 0) ptx::tma_store_commit();
-        stg_sel = (stg_sel + 1) % kStgBufs;
       }
       ptx::tc_fence_before_sync();
       ptx::mbar_arrive(ptx::smem_u32(&s_tempty[buf]));
@@ -503,7 +553,7 @@ static int make_fmap_tmap(CUtensorMap* out, const void* base, int dtype, bool tf
 
 // 3-D map over one pyramid level: dims (W2_i, W1, B*H), box = (128 >> i bytes) x 32 rows x 1,
 // swizzle matched to the box row width (the staging tiles of ChunkStage).
-static int make_level_tmap(CUtensorMap* out, const smoe_pyramid_t* pyr, int level) {
+static int make_level_tmap(CUtensorMap* out, const smoe_pyramid_t* pyr, int level, int d) {
   EncodeTiledFn enc = encode_fn();
   SMOE_REQUIRE(enc != nullptr, SMOE_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   const int es = dtype_size(pyr->dtype);
@@ -511,14 +561,14 @@ static int make_level_tmap(CUtensorMap* out, const smoe_pyramid_t* pyr, int leve
                               (cuuint64_t)pyr->B * pyr->H};
   const cuuint64_t gstr[2] = {(cuuint64_t)pyr->pitch[level] * es,
                               (cuuint64_t)pyr->W1 * pyr->pitch[level] * es};
-  const cuuint32_t box[3] = {(cuuint32_t)((128 >> level) / es), 32u, 1u};
+  const cuuint32_t box[3] = {(cuuint32_t)((128 >> d) / es), 32u, 1u};
   const cuuint32_t estr[3] = {1u, 1u, 1u};
   static const CUtensorMapSwizzle kSw[4] = {CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_SWIZZLE_64B,
                                             CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_SWIZZLE_NONE};
   const CUresult r = enc(out, pyr->dtype == SMOE_DTYPE_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
                                                            : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
                          3, pyr->level_ptr[level], gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         kSw[level], CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                         kSw[d], CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SMOE_REQUIRE(r == CUDA_SUCCESS, SMOE_ERR_CUDA,
                "cuTensorMapEncodeTiled (pyramid level %d) failed with CUresult %d", level, (int)r);
   return SMOE_OK;
@@ -530,14 +580,14 @@ template <typename IT, typename OT>
 static int launch_build(const CUtensorMap& ta, const CUtensorMap& tb, const OutMaps& om, int num_levels,
                         const BuildDims& dims, cudaStream_t st) {
   auto kern = corr_build_kernel<IT, OT>;
-  SMOE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)kBuildSmemBytes));
+  const size_t smem_bytes = (size_t)dims.stages * dims.stage_bytes + kBuildSmemFixed;
+  SMOE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   int dev = 0, sms = 0;
   SMOE_CUDA_OK(cudaGetDevice(&dev));
   SMOE_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const long long items = (long long)dims.BH * dims.MT * dims.NT;
   const int grid = (int)(items < sms ? items : sms);
-  SMOE_CUDA_OK(launch_kernel(kern, dim3(grid), dim3(kBuildThreads), kBuildSmemBytes, st, ta, tb, om,
+  SMOE_CUDA_OK(launch_kernel(kern, dim3(grid), dim3(kBuildThreads), smem_bytes, st, ta, tb, om,
                              num_levels, dims, g_timeline));
   return check_launch("corr_build_kernel");
 }
@@ -641,6 +691,20 @@ int smoe_corr_build(const void* fmap1, const void* fmap2, int in_dtype, int B, i
     dims.BN = ((W2 + dims.NT - 1) / dims.NT + cc - 1) / cc * cc;
     if (dims.BN > kBlockN) dims.BN = kBlockN;
   }
+  dims.debug = 0;
+  if (kProbes) {
+    const char* e = getenv("SMOE_CORR_BUILD_DEBUG");
+    dims.debug = e ? atoi(e) : 0;
+  }
+  {
+    // B slabs (128 bytes of W2 each) one N tile needs -> bytes per stage -> ring depth
+    const int slab = 128 / es;
+    dims.stage_bytes = kStageABytes + (dims.BN + slab - 1) / slab * (kStageBBytes / (kBlockN / slab));
+    dims.stages = (kMaxSmemBytes - kBuildSmemFixed) / dims.stage_bytes;
+    if (dims.stages > kMaxStages) dims.stages = kMaxStages;
+    const char* e = getenv("SMOE_CORR_BUILD_STAGES");      // experiment switch
+    if (e && atoi(e) >= 2 && atoi(e) < dims.stages) dims.stages = atoi(e);
+  }
   dims.denom = denom;
   dims.rcp = 1.0f / denom;
   {
@@ -652,7 +716,9 @@ int smoe_corr_build(const void* fmap1, const void* fmap2, int in_dtype, int B, i
   while (levels > 1 && pyr->width[levels - 1] == 0) --levels;
   OutMaps om;
   for (int i = 0; i < SMOE_MAX_LEVELS; ++i)
-    if (int rc = make_level_tmap(&om.lvl[i], pyr, i < levels ? i : 0)) return rc;
+    for (int d = 0; d <= i; ++d)
+      if (int rc = make_level_tmap(&om.m[OutMaps::index(i, d)], pyr, i < levels ? i : 0, i < levels ? d : 0))
+        return rc;
   if (in_dtype == SMOE_DTYPE_F32 && pyr->dtype == SMOE_DTYPE_F16)      // opt-in fp16 storage
     return launch_build<float, __half>(ta, tb, om, levels, dims, st);
   if (in_dtype == SMOE_DTYPE_F32) return launch_build<float, float>(ta, tb, om, levels, dims, st);
