@@ -15,11 +15,12 @@
 //   warp 1      allocates TMEM (2 x 256 fp32 columns) and issues tcgen05.mma
 //               (kind::tf32 for fp32 inputs, kind::f16 for fp16 inputs), fp32 accumulate.
 //   warps 2-5   epilogue: tcgen05.ld 32 columns at a time, divide, build the three pooled levels
-//               in registers (pooling runs along N == along a thread's own TMEM row), stage the
-//               four levels of a 128-byte-wide column chunk in swizzled shared memory and write
-//               them with TMA tensor stores (full-line writes; TMA clips the W1/W2 tails, so
-//               floor-halving of odd widths needs no masking).  Accumulators are double buffered
-//               so this overlaps the next item's loads and MMAs.
+//               in registers (pooling runs along N == along a thread's own TMEM row), transpose
+//               through swizzled shared-memory tiles and write whole 128-byte row segments with
+//               coalesced 16-byte stores; the narrow rows of the coarse levels are gathered over
+//               several chunks first (GroupPlan).  Accumulators are double buffered so this
+//               overlaps the next item's loads and MMAs.
+// A CTA-pair variant (kPair, tcgen05 cta_group::2) is selectable; see the kernel comment.
 #include <cuda.h>
 #include <math.h>
 #include <stdlib.h>
@@ -50,11 +51,11 @@ constexpr int kMaxSmemBytes = 226 * 1024; // dynamic shared memory budget (227 K
 constexpr int kBuildThreads = 64 + 32 * kEpiWarps;
 constexpr int kTmemCols = 512;
 // epilogue staging: per warp one 4 KiB tile per pyramid level (32 rows x up to 128 bytes).
-// Level 0 leaves as one 128-byte-wide box per chunk.  A coarser level i only produces 128>>i bytes
-// per row and chunk; rows that narrow are expensive to store (a 16-byte row is half a DRAM
-// sector: every level-3 row cost a read-modify-write, and TMA cost is per row, not per byte --
-// profiles/r01/README.md), so the chunks of a level are gathered over up to 2^i chunks and leave
-// as one wider box (see GroupPlan).
+// Level 0 leaves as 128-byte row segments per chunk.  A coarser level i only produces 128>>i
+// bytes per row and chunk; rows that narrow are expensive to store (a 16-byte row is half a DRAM
+// sector: stored per chunk, level 3 alone cost as much as level 0 -- profiles/r01/README.md),
+// so the chunks of a level are gathered over up to 2^i chunks and leave as one wider segment
+// (see GroupPlan).
 constexpr int kStgLevelBytes = 4096;
 constexpr int kStgBytes = SMOE_MAX_LEVELS * kStgLevelBytes;
 constexpr int kStgPerWarp = kStgBytes;
@@ -87,6 +88,7 @@ struct BuildDims {
   int rcp_exact;
   int stages;                // operand ring: depth and bytes per stage (A 16 KiB + the B slabs
   int stage_bytes;           // one N tile needs), sized to fill shared memory
+  int pair;                  // CTA-pair kernel (MT counts 256-row tiles)
   int debug;                 // probe builds only (kProbes)
 };
 
@@ -122,9 +124,9 @@ struct Scaler {
 };
 
 // ------------------------------------------------------------------------------------ epilogue
-// Staging tile of width class d for one warp: 32 rows x (128 >> d) bytes, dense, with the TMA
-// swizzle of that row width (128B / 64B / 32B / none) applied to the 16-byte chunk index so that
-// the 32 lanes (one row each) write without bank conflicts.
+// Staging tile of width class d for one warp: 32 rows x (128 >> d) bytes, dense, with an XOR
+// swizzle of the 16-byte piece index (the 128B / 64B / 32B patterns TMA uses) so that the 32
+// lanes (one row each) write without bank conflicts.
 __device__ __forceinline__ uint32_t stg_addr(uint32_t tile, int d, int row, int byte_off) {
   const uint32_t lin = (uint32_t)row * (128u >> d) + (uint32_t)byte_off;
   const uint32_t mask = (8u >> d) - 1u;
@@ -133,9 +135,9 @@ __device__ __forceinline__ uint32_t stg_addr(uint32_t tile, int d, int row, int 
 // Where chunk c of a tile with `chunks` chunks puts its level-i output.  Chunks are gathered into
 // aligned power-of-two groups of at most 2^i chunks that lie inside the tile (buddy
 // decomposition: 5 chunks at level 3 -> groups of 4 + 1); a group of 2^k chunks is stored as one
-// box of width class d = i - k (row = 128 >> d bytes) once its last chunk has been staged.
+// tile of width class d = i - k (row = 128 >> d bytes) once its last chunk has been staged.
 struct GroupPlan {
-  int d[SMOE_MAX_LEVELS];       // width class of the group's staging tile / tensor map
+  int d[SMOE_MAX_LEVELS];       // width class of the group's staging tile
   int off[SMOE_MAX_LEVELS];     // byte offset of this chunk inside a staged row
   int first[SMOE_MAX_LEVELS];   // first chunk of the group
   bool flush[SMOE_MAX_LEVELS];  // this chunk completes the group
@@ -270,18 +272,50 @@ template <> struct ChunkStage<__half> {
   }
 };
 
-struct OutMaps {
-  // 3-D (W2_i, W1, B*H) maps of pyramid level i with a box of width class d (128 >> d bytes x 32
-  // rows), d <= i: index i*(i+1)/2 + d
-  CUtensorMap m[SMOE_MAX_LEVELS * (SMOE_MAX_LEVELS + 1) / 2];
-  __host__ __device__ static constexpr int index(int level, int d) { return level * (level + 1) / 2 + d; }
-};
+__device__ __forceinline__ uint4 ld_shared_v4u(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+// Copy one staged tile (width class d: 32 rows x (128 >> d) bytes) to global memory with plain
+// coalesced 16-byte stores: 8 >> d lanes cover one row, so every warp instruction writes
+// 4 << d whole row segments.  `grow0` points at (first row of the warp, column 0) of the level,
+// col0 (elements, a multiple of 16 bytes) is where the tile starts.  Columns at or beyond the
+// level width are dropped per 16-byte piece; the pitch rule of smoe_corr_build guarantees that a
+// piece which starts inside the row ends inside its padding.
+template <typename OT>
+__device__ __forceinline__ void store_staged_tile(uint32_t tile, int d, OT* __restrict__ grow0,
+                                                  long long pitch, int col0, int width, int rows_valid,
+                                                  int lane) {
+  constexpr int kPer16 = 16 / (int)sizeof(OT);
+  const int ppr = 8 >> d;                       // 16-byte pieces per staged row
+  const int piece = lane & (ppr - 1);
+  const int rsub = lane >> (3 - d);             // row inside one pass
+  const int col = col0 + piece * kPer16;
+  const bool col_ok = col < width;
+  uint4 v[8];
+#pragma unroll
+  for (int p = 0; p < 8; ++p)
+    if (p < ppr) v[p] = ld_shared_v4u(stg_addr(tile, d, p * (4 << d) + rsub, piece * 16));
+#pragma unroll
+  for (int p = 0; p < 8; ++p) {
+    const int row = p * (4 << d) + rsub;
+    if (p < ppr && col_ok && row < rows_valid)
+      *reinterpret_cast<uint4*>(grow0 + (long long)row * pitch + col) = v[p];
+  }
+}
 
 // -------------------------------------------------------------------------------------- kernel
-template <typename IT, typename OT>
+// kPair: the kernel runs as clusters of two CTAs (one TPC) that compute one 256-row M tile with
+// tcgen05.mma.cta_group::2.  Each CTA loads its own 128 rows of A and only HALF of the B columns
+// -- the tensor cores read both halves through the pair's shared memory -- so a B row slab is
+// fetched from L2 once per 256 output rows instead of once per 128.  Rank 0 (the leader) owns
+// the `full` and `accumulator empty` barriers and issues the MMAs; both CTAs run their own
+// producer and epilogue; `empty` / `accumulator full` arrive in both CTAs by multicast commit.
+template <typename IT, typename OT, bool kPair>
 __global__ void __launch_bounds__(kBuildThreads, 1)
 corr_build_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                  const __grid_constant__ OutMaps omaps, const int num_levels, const BuildDims dims,
+                  const PyrDev out, const int num_levels, const BuildDims dims,
                   long long* __restrict__ timeline) {
   using Cfg = OperandCfg<IT>;
   constexpr int kSlabBytes = Cfg::kKT * 128;                 // one W slab x KT channels
@@ -305,27 +339,34 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_items = dims.BH * dims.MT * dims.NT;
   const int num_k = (dims.C + Cfg::kKT - 1) / Cfg::kKT;
+  const uint32_t rank = kPair ? ptx::cluster_ctarank() : 0u;             // CTA within the pair
+  const int worker = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // item walker (CTA or pair)
+  const int workers = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmap_a);
     ptx::prefetch_tensormap(&tmap_b);
-    for (int i = 0; i < OutMaps::index(num_levels, 0); ++i) ptx::prefetch_tensormap(&omaps.m[i]);
     for (int i = 0; i < dims.stages; ++i) {
       ptx::mbar_init(ptx::smem_u32(&s_full[i]), 1);
       ptx::mbar_init(ptx::smem_u32(&s_empty[i]), 1);
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(ptx::smem_u32(&s_tfull[i]), 1);
-      ptx::mbar_init(ptx::smem_u32(&s_tempty[i]), 32 * kEpiWarps);
+      ptx::mbar_init(ptx::smem_u32(&s_tempty[i]), kEpiWarps * (kPair ? 2 : 1));   // lane 0 of each warp
     }
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc(ptx::smem_u32(&s_tmem_base), kTmemCols);
-    ptx::tmem_relinquish();
+    if (kPair) {
+      ptx::tmem_alloc_pair(ptx::smem_u32(&s_tmem_base), kTmemCols);
+      ptx::tmem_relinquish_pair();
+    } else {
+      ptx::tmem_alloc(ptx::smem_u32(&s_tmem_base), kTmemCols);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before_sync();
-  __syncthreads();
+  if (kPair) ptx::cluster_sync(); else __syncthreads();   // peer barriers are initialised too
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = s_tmem_base;
   // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) may overlap the
@@ -340,32 +381,47 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       uint32_t phase = 0;
       int it = 0;
       stamp(0, 0);
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
+      for (int item = worker; item < total_items; item += workers, ++it) {
         const int nt = item % dims.NT;
         const int mt = (item / dims.NT) % dims.MT;
         const int bh = item / (dims.NT * dims.MT);
         const int b = bh / dims.H, h = bh - b * dims.H;
         const int n_valid = min(dims.BN, dims.W2 - nt * dims.BN);
-        const int slabs_b = (n_valid + Cfg::kSlab - 1) / Cfg::kSlab;
-        const uint32_t tx_bytes = (uint32_t)(kSlabsA + slabs_b) * kSlabBytes;
+        // pair: this CTA's half of the N tile (whole slabs), leader expects both CTAs' bytes
+        const int slabs_b = kPair ? (n_valid + 2 * Cfg::kSlab - 1) / (2 * Cfg::kSlab)
+                                  : (n_valid + Cfg::kSlab - 1) / Cfg::kSlab;
+        const uint32_t tx_bytes = (uint32_t)(kSlabsA + slabs_b) * kSlabBytes * (kPair ? 2u : 1u);
+        const int a_row0 = (kPair ? mt * 2 + (int)rank : mt) * kBlockM;
+        const int b_col0 = nt * dims.BN + (kPair ? (int)rank * slabs_b * Cfg::kSlab : 0);
         for (int ks = 0; ks < num_k; ++ks) {
           ptx::mbar_wait(ptx::smem_u32(&s_empty[stage]), phase ^ 1u);
-          const uint32_t full = ptx::smem_u32(&s_full[stage]);
+          const uint32_t full_local = ptx::smem_u32(&s_full[stage]);
           if (kProbes && (dims.debug & 1)) {
-            ptx::mbar_arrive(full);
+            if (rank == 0) ptx::mbar_arrive(full_local);
             if (++stage == dims.stages) { stage = 0; phase ^= 1u; }
             continue;
           }
-          ptx::mbar_expect_tx(full, tx_bytes);
+          if (rank == 0) ptx::mbar_expect_tx(full_local, tx_bytes);
+          const uint32_t full = kPair ? ptx::map_to_cta(full_local, 0) : full_local;
           const uint32_t sa = smem_base + stage * dims.stage_bytes;
           const uint32_t sb = sa + kStageABytes;
+          if (kPair) {
 #pragma unroll
-          for (int j = 0; j < kSlabsA; ++j)
-            ptx::tma_load_4d(sa + j * kSlabBytes, &tmap_a, full, mt * kBlockM + j * Cfg::kSlab, h,
-                             ks * Cfg::kKT, b);
-          for (int j = 0; j < slabs_b; ++j)
-            ptx::tma_load_4d(sb + j * kSlabBytes, &tmap_b, full, nt * dims.BN + j * Cfg::kSlab, h,
-                             ks * Cfg::kKT, b);
+            for (int j = 0; j < kSlabsA; ++j)
+              ptx::tma_load_4d_pair(sa + j * kSlabBytes, &tmap_a, full, a_row0 + j * Cfg::kSlab, h,
+                                    ks * Cfg::kKT, b);
+            for (int j = 0; j < slabs_b; ++j)
+              ptx::tma_load_4d_pair(sb + j * kSlabBytes, &tmap_b, full, b_col0 + j * Cfg::kSlab, h,
+                                    ks * Cfg::kKT, b);
+          } else {
+#pragma unroll
+            for (int j = 0; j < kSlabsA; ++j)
+              ptx::tma_load_4d(sa + j * kSlabBytes, &tmap_a, full, a_row0 + j * Cfg::kSlab, h,
+                               ks * Cfg::kKT, b);
+            for (int j = 0; j < slabs_b; ++j)
+              ptx::tma_load_4d(sb + j * kSlabBytes, &tmap_b, full, b_col0 + j * Cfg::kSlab, h,
+                               ks * Cfg::kKT, b);
+          }
           if (++stage == dims.stages) { stage = 0; phase ^= 1u; }
         }
         stamp(0, 1 + it);                 // all loads of item `it` issued
@@ -373,18 +429,21 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
+    if (lane == 0 && rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       int buf = 0;
       uint32_t bphase = 0;
       int it = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
+      for (int item = worker; item < total_items; item += workers, ++it) {
         const int nt = item % dims.NT;
         const int n_valid = min(dims.BN, dims.W2 - nt * dims.BN);
-        const uint32_t n_mma = (uint32_t)((n_valid + 15) & ~15);
-        const uint32_t idesc = ptx::make_idesc_mn_major(Cfg::kFmt, kBlockM, n_mma);
-        ptx::mbar_wait(ptx::smem_u32(&s_tempty[buf]), bphase ^ 1u);
+        const uint32_t n_mma =
+            kPair ? (uint32_t)((n_valid + 2 * Cfg::kSlab - 1) / (2 * Cfg::kSlab) * (2 * Cfg::kSlab))
+                  : (uint32_t)((n_valid + 15) & ~15);
+        const uint32_t idesc = ptx::make_idesc_mn_major(Cfg::kFmt, kPair ? 2 * kBlockM : kBlockM, n_mma);
+        if (kPair) ptx::mbar_wait_cluster(ptx::smem_u32(&s_tempty[buf]), bphase ^ 1u);
+        else ptx::mbar_wait(ptx::smem_u32(&s_tempty[buf]), bphase ^ 1u);
         ptx::tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + (uint32_t)buf * kBlockN;
         for (int ks = 0; ks < num_k; ++ks) {
@@ -401,15 +460,20 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 ptx::make_smem_desc(sa + kk * kKStepBytes, kSlabBytes, Cfg::kSBO, Cfg::kLayout);
             const uint64_t bdesc =
                 ptx::make_smem_desc(sb + kk * kKStepBytes, kSlabBytes, Cfg::kSBO, Cfg::kLayout);
-            if (sizeof(IT) == 4)
+            if (kPair)
+              ptx::mma_pair<sizeof(IT) == 4>(d_tmem, adesc, bdesc, idesc, (ks | kk) != 0 ? 1u : 0u);
+            else if (sizeof(IT) == 4)
               ptx::mma_tf32(d_tmem, adesc, bdesc, idesc, (ks | kk) != 0 ? 1u : 0u);
             else
               ptx::mma_f16(d_tmem, adesc, bdesc, idesc, (ks | kk) != 0 ? 1u : 0u);
           }
-          ptx::tc_commit(ptx::smem_u32(&s_empty[stage]));     // smem slot free when MMAs retire
+          // smem slot free (in both CTAs of a pair) when the MMAs retire
+          if (kPair) ptx::tc_commit_pair(ptx::smem_u32(&s_empty[stage]));
+          else ptx::tc_commit(ptx::smem_u32(&s_empty[stage]));
           if (++stage == dims.stages) { stage = 0; phase ^= 1u; }
         }
-        ptx::tc_commit(ptx::smem_u32(&s_tfull[buf]));          // accumulator ready
+        if (kPair) ptx::tc_commit_pair(ptx::smem_u32(&s_tfull[buf]));   // accumulator ready
+        else ptx::tc_commit(ptx::smem_u32(&s_tfull[buf]));
         stamp(1, 3 * it + 2);
         buf ^= 1;
         if (buf == 0) bphase ^= 1u;
@@ -421,18 +485,17 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     constexpr int kChunkCols = 32 * kSub;
     const int quad = warp & 3;                    // TMEM lane quadrant this warp may read
     const Scaler sc{dims.denom, dims.rcp, dims.rcp_exact};
-    // staging tiles are 1 KiB aligned (smem_base is, stages and tiles are KiB multiples): the
-    // swizzle XOR in stg_addr then equals the TMA's function of the absolute address
     const uint32_t stg_base = smem_base + dims.stages * dims.stage_bytes + (uint32_t)(warp - 2) * kStgPerWarp;
     int buf = 0;
     uint32_t bphase = 0;
     int it = 0;
-    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
+    long long probe_sum[5] = {0, 0, 0, 0, 0};
+    for (int item = worker; item < total_items; item += workers, ++it) {
       const int nt = item % dims.NT;
       const int mt = (item / dims.NT) % dims.MT;
       const int bh = item / (dims.NT * dims.MT);
       const int n_valid = min(dims.BN, dims.W2 - nt * dims.BN);
-      const int m0 = mt * kBlockM + quad * 32;          // first output row of this warp
+      const int m0 = (kPair ? mt * 2 + (int)rank : mt) * kBlockM + quad * 32;   // first output row of this warp
       ptx::mbar_wait(ptx::smem_u32(&s_tfull[buf]), bphase);
       ptx::tc_fence_after_sync();
       if (warp == 2 && lane == 0) stamp(2, 2 * it);          // accumulator of the item complete
@@ -440,45 +503,60 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const int chunks = (n_valid + kChunkCols - 1) / kChunkCols;
       for (int c = 0; c < chunks; ++c) {
         const GroupPlan gp(c, chunks);
-        // the TMA stores that last read the staging tiles must have drained
-        if (lane == 0) ptx::tma_store_wait_read<0>();
-        __syncwarp();
+        long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+        if (kProbes) t0 = clock64();
+        if (kProbes) t1 = clock64();
 #pragma unroll
         for (int sub = 0; sub < kSub; ++sub) {
           if (c * kChunkCols + sub * 32 < n_valid || sub == 0) {
             uint32_t acc[32];
             ptx::tmem_ld_32x32(taddr + c * kChunkCols + sub * 32, acc);
             ptx::tmem_ld_wait();
+            if (kProbes && sub == 0) t2 = clock64();
             ChunkStage<OT>::template run<sizeof(IT) == 2>(acc, stg_base, lane, sub, sc, num_levels, gp);
           }
         }
-        ptx::fence_proxy_async_smem();             // generic-proxy smem writes -> async proxy (TMA)
-        __syncwarp();
-        if (lane == 0 && m0 < dims.W1 && !(kProbes && (dims.debug & 2))) {
+        __syncwarp();                                // staged tiles visible to the whole warp
+        if (kProbes) t3 = clock64();
+        const int rows_valid = dims.W1 - m0;
+        if (rows_valid > 0 && !(kProbes && (dims.debug & 2))) {
           const int n0 = nt * dims.BN;
+          const long long grow = (long long)bh * dims.W1 + m0;
 #pragma unroll
           for (int i = 0; i < SMOE_MAX_LEVELS; ++i)
             if (i < num_levels && gp.flush[i])
-              ptx::tma_store_3d(&omaps.m[OutMaps::index(i, gp.d[i])], stg_base + i * kStgLevelBytes,
-                                (n0 + gp.first[i] * kChunkCols) >> i, m0, bh);
+              store_staged_tile<OT>(stg_base + i * kStgLevelBytes, i == 0 ? 0 : gp.d[i],
+                                    static_cast<OT*>(out.ptr[i]) + grow * out.pitch[i], out.pitch[i],
+                                    (n0 + gp.first[i] * kChunkCols) >> i, out.width[i], rows_valid, lane);
         }
-        if (lane == 0) ptx::tma_store_commit();
+        __syncwarp();                                // tiles may be overwritten by the next chunk
+        if (kProbes) {      // per-phase cycle sums: store drain wait, TMEM load, stage, store issue
+          const long long t4 = clock64();
+          probe_sum[0] += t1 - t0; probe_sum[1] += t2 - t1; probe_sum[2] += t3 - t2; probe_sum[3] += t4 - t3;
+          probe_sum[4] += 1;
+        }
       }
       ptx::tc_fence_before_sync();
-      ptx::mbar_arrive(ptx::smem_u32(&s_tempty[buf]));
+      __syncwarp();
+      if (lane == 0) {                               // this warp has drained the accumulator
+        if (kPair) ptx::mbar_arrive_cluster(ptx::map_to_cta(ptx::smem_u32(&s_tempty[buf]), 0));
+        else ptx::mbar_arrive(ptx::smem_u32(&s_tempty[buf]));
+      }
       if (warp == 2 && lane == 0) stamp(2, 2 * it + 1);      // epilogue of the item issued
       buf ^= 1;
       if (buf == 0) bphase ^= 1u;
     }
-    if (lane == 0) ptx::tma_store_wait_all<0>();   // global writes complete before the CTA exits
     if (warp == 2 && lane == 0) stamp(2, 15);
+    if (kProbes && warp == 2 && lane == 0 && timeline != nullptr)
+      for (int i = 0; i < 5; ++i) timeline[((long long)blockIdx.x * 3 + 2) * 16 + 9 + i] = probe_sum[i];
   }
 
   ptx::tc_fence_before_sync();
-  __syncthreads();
+  if (kPair) ptx::cluster_sync(); else __syncthreads();   // no CTA leaves while its peer may signal it
   if (warp == 1) {
     ptx::tc_fence_after_sync();
-    ptx::tmem_dealloc(tmem_base, kTmemCols);
+    if (kPair) ptx::tmem_dealloc_pair(tmem_base, kTmemCols);
+    else ptx::tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -551,45 +629,27 @@ static int make_fmap_tmap(CUtensorMap* out, const void* base, int dtype, bool tf
   return SMOE_OK;
 }
 
-// 3-D map over one pyramid level: dims (W2_i, W1, B*H), box = (128 >> i bytes) x 32 rows x 1,
-// swizzle matched to the box row width (the staging tiles of ChunkStage).
-static int make_level_tmap(CUtensorMap* out, const smoe_pyramid_t* pyr, int level, int d) {
-  EncodeTiledFn enc = encode_fn();
-  SMOE_REQUIRE(enc != nullptr, SMOE_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
-  const int es = dtype_size(pyr->dtype);
-  const cuuint64_t gdim[3] = {(cuuint64_t)pyr->width[level], (cuuint64_t)pyr->W1,
-                              (cuuint64_t)pyr->B * pyr->H};
-  const cuuint64_t gstr[2] = {(cuuint64_t)pyr->pitch[level] * es,
-                              (cuuint64_t)pyr->W1 * pyr->pitch[level] * es};
-  const cuuint32_t box[3] = {(cuuint32_t)((128 >> d) / es), 32u, 1u};
-  const cuuint32_t estr[3] = {1u, 1u, 1u};
-  static const CUtensorMapSwizzle kSw[4] = {CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_SWIZZLE_64B,
-                                            CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_SWIZZLE_NONE};
-  const CUresult r = enc(out, pyr->dtype == SMOE_DTYPE_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
-                                                           : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
-                         3, pyr->level_ptr[level], gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         kSw[d], CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  SMOE_REQUIRE(r == CUDA_SUCCESS, SMOE_ERR_CUDA,
-               "cuTensorMapEncodeTiled (pyramid level %d) failed with CUresult %d", level, (int)r);
-  return SMOE_OK;
-}
-
 static thread_local long long* g_timeline = nullptr;   // smoe_corr_debug_set_timeline
 
-template <typename IT, typename OT>
-static int launch_build(const CUtensorMap& ta, const CUtensorMap& tb, const OutMaps& om, int num_levels,
-                        const BuildDims& dims, cudaStream_t st) {
-  auto kern = corr_build_kernel<IT, OT>;
+template <typename IT, typename OT, bool kPair>
+static int launch_build_impl(const CUtensorMap& ta, const CUtensorMap& tb, const PyrDev& out, int num_levels, const BuildDims& dims, cudaStream_t st) {
+  auto kern = corr_build_kernel<IT, OT, kPair>;
   const size_t smem_bytes = (size_t)dims.stages * dims.stage_bytes + kBuildSmemFixed;
   SMOE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   int dev = 0, sms = 0;
   SMOE_CUDA_OK(cudaGetDevice(&dev));
   SMOE_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const long long items = (long long)dims.BH * dims.MT * dims.NT;
-  const int grid = (int)(items < sms ? items : sms);
-  SMOE_CUDA_OK(launch_kernel(kern, dim3(grid), dim3(kBuildThreads), smem_bytes, st, ta, tb, om,
-                             num_levels, dims, g_timeline));
+  const int workers = kPair ? sms / 2 : sms;            // persistent CTAs (or CTA pairs)
+  const int grid = (int)(items < workers ? items : workers) * (kPair ? 2 : 1);
+  SMOE_CUDA_OK(launch_kernel_cluster(kern, dim3(grid), dim3(kBuildThreads), smem_bytes, st,
+                                     kPair ? 2u : 1u, ta, tb, out, num_levels, dims, g_timeline));
   return check_launch("corr_build_kernel");
+}
+template <typename IT, typename OT>
+static int launch_build(const CUtensorMap& ta, const CUtensorMap& tb, const PyrDev& out, int num_levels, const BuildDims& dims, cudaStream_t st) {
+  return dims.pair ? launch_build_impl<IT, OT, true>(ta, tb, out, num_levels, dims, st)
+                   : launch_build_impl<IT, OT, false>(ta, tb, out, num_levels, dims, st);
 }
 
 }  // namespace smoe
@@ -684,10 +744,15 @@ int smoe_corr_build(const void* fmap1, const void* fmap2, int in_dtype, int B, i
 
   BuildDims dims;
   dims.W1 = W1; dims.W2 = W2; dims.C = C; dims.H = H; dims.BH = B * H;
-  dims.MT = (W1 + kBlockM - 1) / kBlockM;
+  {
+    const char* e = getenv("SMOE_CORR_BUILD_PAIR");
+    dims.pair = e ? atoi(e) : 0;
+  }
+  dims.MT = (W1 + (dims.pair ? 2 : 1) * kBlockM - 1) / ((dims.pair ? 2 : 1) * kBlockM);
   dims.NT = (W2 + kBlockN - 1) / kBlockN;
   {
-    const int cc = 128 / oes;   // columns per 128-byte epilogue chunk: 32 (fp32 out) / 64 (fp16 out)
+    int cc = 128 / oes;   // columns per 128-byte epilogue chunk: 32 (fp32 out) / 64 (fp16 out)
+    if (dims.pair && cc < 2 * (128 / es)) cc = 2 * (128 / es);   // two whole B slabs per pair
     dims.BN = ((W2 + dims.NT - 1) / dims.NT + cc - 1) / cc * cc;
     if (dims.BN > kBlockN) dims.BN = kBlockN;
   }
@@ -699,7 +764,8 @@ int smoe_corr_build(const void* fmap1, const void* fmap2, int in_dtype, int B, i
   {
     // B slabs (128 bytes of W2 each) one N tile needs -> bytes per stage -> ring depth
     const int slab = 128 / es;
-    dims.stage_bytes = kStageABytes + (dims.BN + slab - 1) / slab * (kStageBBytes / (kBlockN / slab));
+    const int bn_cta = dims.pair ? dims.BN / 2 : dims.BN;          // B columns one CTA stages
+    dims.stage_bytes = kStageABytes + (bn_cta + slab - 1) / slab * (kStageBBytes / (kBlockN / slab));
     dims.stages = (kMaxSmemBytes - kBuildSmemFixed) / dims.stage_bytes;
     if (dims.stages > kMaxStages) dims.stages = kMaxStages;
     const char* e = getenv("SMOE_CORR_BUILD_STAGES");      // experiment switch
@@ -714,16 +780,12 @@ int smoe_corr_build(const void* fmap1, const void* fmap2, int in_dtype, int B, i
   // levels whose width has shrunk to 0 have nothing to write
   int levels = pyr->num_levels;
   while (levels > 1 && pyr->width[levels - 1] == 0) --levels;
-  OutMaps om;
-  for (int i = 0; i < SMOE_MAX_LEVELS; ++i)
-    for (int d = 0; d <= i; ++d)
-      if (int rc = make_level_tmap(&om.m[OutMaps::index(i, d)], pyr, i < levels ? i : 0, i < levels ? d : 0))
-        return rc;
+  const PyrDev pd = to_dev(pyr);
   if (in_dtype == SMOE_DTYPE_F32 && pyr->dtype == SMOE_DTYPE_F16)      // opt-in fp16 storage
-    return launch_build<float, __half>(ta, tb, om, levels, dims, st);
-  if (in_dtype == SMOE_DTYPE_F32) return launch_build<float, float>(ta, tb, om, levels, dims, st);
-  if (pyr->dtype == SMOE_DTYPE_F16) return launch_build<__half, __half>(ta, tb, om, levels, dims, st);
-  return launch_build<__half, float>(ta, tb, om, levels, dims, st);
+    return launch_build<float, __half>(ta, tb, pd, levels, dims, st);
+  if (in_dtype == SMOE_DTYPE_F32) return launch_build<float, float>(ta, tb, pd, levels, dims, st);
+  if (pyr->dtype == SMOE_DTYPE_F16) return launch_build<__half, __half>(ta, tb, pd, levels, dims, st);
+  return launch_build<__half, float>(ta, tb, pd, levels, dims, st);
 }
 
 }  // extern "C"

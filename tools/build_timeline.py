@@ -35,3 +35,10 @@ if os.environ.get("TL_RAW"):
         print("  producer", t[cta, 0])
         print("  mma     ", t[cta, 1])
         print("  epilogue", t[cta, 2])
+if os.environ.get("TL_PROBE"):
+    # probe builds (-DSMOE_BUILD_PROBES): warp 2's per-chunk cycle sums, slots 9..13 of role 2
+    raw = tl.cpu().numpy().reshape(148, 3, 16)[:, 2, 9:14].astype(np.float64)
+    raw = raw[raw[:, 4] > 0]
+    per = raw[:, :4] / raw[:, 4:5]
+    print("epilogue cycles per chunk (median over CTAs): store-drain wait %.0f | tmem ld %.0f | scale+pool+stage+fence %.0f | store issue %.0f | chunks/CTA %.0f"
+          % (*np.median(per, axis=0), np.median(raw[:, 4])))
