@@ -16,6 +16,8 @@
  *                              (CorrBlockFast1D.__call__), sampler/sampler.cpp:24-32 and
  *                              sampler/sampler_kernel.cu:19-60,107-136 (corr_sampler.forward)
  *   smoe_corr_lookup_update    the loop glue of core/SMoEStereo.py:234-248 + the lookup (opt-in)
+ *   smoe_corr_lookup_conv1x1   the lookup + BasicMotionEncoder.convc1 + ReLU, core/update.py:70,77
+ *                              (opt-in)
  *   smoe_corr_lookup_bwd       sampler/sampler.cpp:34-45, sampler/sampler_kernel.cu:63-105,138-166
  *                              (corr_sampler.backward)
  *   smoe_corr_fold_pyramid_grad  autograd of core/corr.py:122-125 (avg_pool2d backward chain)
@@ -147,6 +149,28 @@ int smoe_corr_lookup(const smoe_pyramid_t* pyr, const float* coords, int64_t coo
 int smoe_corr_lookup_update(const smoe_pyramid_t* pyr, const float* coords1, const float* delta_flow,
                             const float* coords0, float* coords1_out, float* flow_out, int radius,
                             void* out, int out_dtype, smoe_stream_t stream);
+
+/*
+ * Lookup fused with the 1x1 convolution that consumes it (opt-in extension):
+ *   out[b,o,y,x] = act( bias[o] + sum_j weight[o,j] * lookup(pyr, coords)[b,j,y,x] )
+ * which is `F.relu(self.convc1(corr))` of the reference's motion encoder (core/update.py:70,77,
+ * Conv2d(L*(2r+1), 64, kernel 1)) applied to what smoe_corr_lookup would have returned; the
+ * L*(2r+1)-channel lookup result never reaches global memory.  Inference only (no backward).
+ *   lookup_dtype  arithmetic/rounding of the lookup stage = the out_dtype smoe_corr_lookup would be
+ *                 called with (fp32 for CorrBlock1D, the volume dtype for CorrBlockFast1D)
+ *   weight        (cout, L*(2r+1)) fp32 contiguous (Conv2d.weight viewed 2-D); bias (cout) fp32 or NULL
+ *   relu          non-zero: act = max(.,0); zero: identity
+ *   out           (B, cout, H, W1) contiguous, out_dtype
+ * The products run on the tensor cores in tf32 (lookup values and weights rounded to nearest,
+ * fp32 accumulate): ~3e-4 relative to an fp32 convolution, exact to fp16-rounding when the
+ * reference runs this layer under autocast.  Supported: radius 4, cout a multiple of 16 up to 256,
+ * 16-byte aligned levels (smoe_corr_pyramid_layout); otherwise SMOE_ERR_UNSUPPORTED -- run
+ * smoe_corr_lookup and the convolution separately.
+ */
+int smoe_corr_lookup_conv1x1(const smoe_pyramid_t* pyr, const float* coords,
+                             int64_t coords_batch_stride, float coord_scale, int radius,
+                             int lookup_dtype, const float* weight, const float* bias, int cout,
+                             int relu, void* out, int out_dtype, smoe_stream_t stream);
 
 /*
  * Lookup backward (gradient w.r.t. the pyramid levels; coords get no gradient, core/corr.py:29).

@@ -130,6 +130,18 @@ def numpy_lookup(levels: list[np.ndarray], coords: np.ndarray, radius: int) -> n
     return np.concatenate(outs, axis=1)
 
 
+def numpy_conv1x1(corr: np.ndarray, weight: np.ndarray, bias, relu: bool = True) -> np.ndarray:
+    """The layer that consumes the lookup: `F.relu(self.convc1(corr))`, a 1x1 Conv2d
+    (core/update.py:70,77).  corr (B,Cin,H,W), weight (Cout,Cin), bias (Cout,) or None; fp32
+    products accumulated in fp64 and rounded once (the reference accumulates in fp32)."""
+    y = np.einsum("oc,bchw->bohw", weight.astype(np.float64), corr.astype(np.float64))
+    if bias is not None:
+        y = y + np.asarray(bias, dtype=np.float64)[None, :, None, None]
+    if relu:
+        y = np.maximum(y, 0.0)
+    return y.astype(np.float32)
+
+
 def numpy_lookup_level_bwd(coords_x: np.ndarray, grad: np.ndarray, W2: int, radius: int) -> np.ndarray:
     """Transpose of numpy_lookup_level: (B,2r+1,H,W1) -> (B,H,W1,W2); sampler_kernel.cu:83-103."""
     B, _, H, W1 = grad.shape

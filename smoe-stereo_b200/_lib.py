@@ -26,7 +26,7 @@ SYMBOLS = (
     "smoe_corr_pyramid_layout", "smoe_corr_build_workspace_bytes", "smoe_corr_build",
     "smoe_corr_lookup", "smoe_corr_lookup_bwd", "smoe_corr_fold_pyramid_grad",
     "smoe_corr_debug_set_timeline", "smoe_corr_build_bwd", "smoe_corr_lookup_update",
-    "smoe_corr_lookup_bwd_batched",
+    "smoe_corr_lookup_bwd_batched", "smoe_corr_lookup_conv1x1",
 )
 
 
@@ -65,6 +65,8 @@ def _declare(L: ctypes.CDLL) -> None:
     L.smoe_corr_lookup_bwd.argtypes = [pp, vp, i64, f32, i32, vp, i32, i32, vp]
     L.smoe_corr_lookup_update.argtypes = [pp, vp, vp, vp, vp, vp, i32, vp, i32, vp]
     L.smoe_corr_lookup_update.restype = i32
+    L.smoe_corr_lookup_conv1x1.argtypes = [pp, vp, i64, f32, i32, i32, vp, vp, i32, i32, vp, i32, vp]
+    L.smoe_corr_lookup_conv1x1.restype = i32
     L.smoe_corr_lookup_bwd_batched.argtypes = [pp, i32, i32, vp, vp, vp, i32, i32, i32, vp]
     L.smoe_corr_lookup_bwd_batched.restype = i32
     L.smoe_corr_fold_pyramid_grad.argtypes = [pp, vp]

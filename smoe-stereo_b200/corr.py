@@ -24,6 +24,7 @@ import math
 import os
 
 import torch
+import torch.nn.functional as F
 
 from . import _lib
 from . import corr_sampler
@@ -418,6 +419,55 @@ class _CorrBlockBase:
                 _DTYPE_CODE[out_dtype], _stream_ptr(p.device))
         _lib.check(rc, "smoe_corr_lookup_update")
         return out, c1_new, flow
+
+    def lookup_conv(self, coords, weight, bias=None, relu=True, out_dtype=None):
+        """Opt-in fused lookup + 1x1 convolution (+bias, +ReLU):
+
+            cor = F.relu(F.conv2d(corr_fn(coords), weight, bias))     # core/update.py:70,77 (convc1)
+
+        in ONE kernel; the L*(2r+1)-channel lookup result is never written.  `weight` is
+        (Cout, L*(2r+1)) or Conv2d-shaped (Cout, L*(2r+1), 1, 1); products run in tf32 on the
+        tensor cores with fp32 accumulation.  `out_dtype` defaults to the dtype an autocast-free
+        F.conv2d on the lookup result would produce.  Shapes the fused kernel does not cover
+        (radius != 4, Cout not a multiple of 16 or > 256) and calls that need gradients run the
+        lookup kernel followed by F.conv2d."""
+        p = self._state.pyr
+        lookup_dtype = torch.float32 if self._float_output else p.dtype
+        cin = p.num_levels * (2 * self.radius + 1)
+        if weight.dim() == 4:
+            if weight.shape[2:] != (1, 1):
+                raise RuntimeError("lookup_conv fuses a 1x1 convolution; weight must be (Cout,Cin,1,1)")
+            weight2d = weight.reshape(weight.shape[0], weight.shape[1])
+        else:
+            weight2d = weight
+        if weight2d.dim() != 2 or weight2d.shape[1] != cin:
+            raise RuntimeError(f"weight must have {cin} input channels, got {tuple(weight.shape)}")
+        cout = weight2d.shape[0]
+        if bias is not None and tuple(bias.shape) != (cout,):
+            raise RuntimeError(f"bias must have shape ({cout},)")
+        if out_dtype is None:
+            out_dtype = lookup_dtype
+        needs_grad = torch.is_grad_enabled() and (
+            self._token is not None or weight.requires_grad or (bias is not None and bias.requires_grad))
+        fusable = (self.radius == 4 and cout % 16 == 0 and 16 <= cout <= 256
+                   and out_dtype in _DTYPE_CODE and not needs_grad)
+        if not fusable:
+            corr = self(coords)
+            w4 = weight2d.reshape(cout, cin, 1, 1).to(corr.dtype)
+            y = F.conv2d(corr, w4, bias.to(corr.dtype) if bias is not None else None)
+            return (F.relu(y) if relu else y).to(out_dtype)
+        _require_cuda(weight2d, "weight")
+        w = weight2d.detach().to(torch.float32).contiguous()
+        bvec = bias.detach().to(torch.float32).contiguous() if bias is not None else None
+        coords, bstride = _coords_plane(coords, p.B, p.H, p.W1)
+        out = torch.empty((p.B, cout, p.H, p.W1), dtype=out_dtype, device=p.device)
+        with _on_device(p.device):
+            rc = _lib.lib().smoe_corr_lookup_conv1x1(
+                p.ref, coords.data_ptr(), bstride, 1.0, self.radius, _DTYPE_CODE[lookup_dtype],
+                w.data_ptr(), bvec.data_ptr() if bvec is not None else None, cout, 1 if relu else 0,
+                out.data_ptr(), _DTYPE_CODE[out_dtype], _stream_ptr(p.device))
+        _lib.check(rc, "smoe_corr_lookup_conv1x1")
+        return out
 
     @staticmethod
     def corr(fmap1, fmap2):

@@ -695,7 +695,7 @@ fold_grad_scalar_kernel(PyrDev gp, long long rows) {
 }
 
 // --------------------------------------------------------------------------------- dispatch
-static bool vec_ok(const smoe_pyramid_t* p) {
+bool pyramid_vec_ok(const smoe_pyramid_t* p) {   // also used by lookup_conv.cu
   const int es = dtype_size(p->dtype);
   for (int i = 0; i < p->num_levels; ++i) {
     if (!aligned16(p->level_ptr[i])) return false;
@@ -803,7 +803,7 @@ static int launch_bwd_dense(const smoe_pyramid_t* gp, const PyrDev& d, const flo
   const size_t smem = ((size_t)gp->num_levels * (2 * R + 1) * (kTilePx + 1) + kTilePx) * sizeof(float);
   SMOE_REQUIRE(smem <= 48 * 1024, SMOE_ERR_UNSUPPORTED, "lookup_bwd: radius %d too large", R);
   constexpr int VEC = 16 / sizeof(VT);
-  bool vec = vec_ok(gp);
+  bool vec = pyramid_vec_ok(gp);
   for (int i = 0; i < gp->num_levels; ++i) vec = vec && (gp->width[i] % VEC == 0);
   if (vec)
     launch_kernel(lookup_bwd_dense_kernel<VT, GT, VEC>, grid, dim3(kDenseThreads), smem, st, d, coords,
@@ -835,7 +835,7 @@ static int lookup_impl(const smoe_pyramid_t* pyr, const float* coords, int64_t c
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const PyrDev d = to_dev(pyr);
   const bool f16v = pyr->dtype == SMOE_DTYPE_F16, f16o = out_dtype == SMOE_DTYPE_F16;
-  if (radius == 4 && vec_ok(pyr)) {
+  if (radius == 4 && pyramid_vec_ok(pyr)) {
     if (!f16v)
       dispatch_fwd_vec<float, float>(pyr->num_levels, d, coords, coords_batch_stride, coord_scale,
                                      out, (int)HW, pyr->B, st, upd);
@@ -909,7 +909,7 @@ int smoe_corr_lookup_bwd(const smoe_pyramid_t* gp, const float* coords, int64_t 
   if (mode == SMOE_BWD_ACCUMULATE) {
     SMOE_REQUIRE(gp->dtype == SMOE_DTYPE_F32, SMOE_ERR_UNSUPPORTED,
                  "lookup_bwd: the accumulating gradient pyramid must be fp32");
-    if (radius == 4 && vec_ok(gp)) {
+    if (radius == 4 && pyramid_vec_ok(gp)) {
       if (f16g)
         dispatch_bwd_acc_vec<__half>(gp->num_levels, d, coords, coords_batch_stride, coord_scale,
                                      grad_out, (int)HW, gp->B, st);

@@ -1,0 +1,272 @@
+// lookup_conv.cu -- pyramid lookup fused with the 1x1 convolution (+bias, +ReLU) that consumes it
+// (SURVEY.md 8f row f2): the first layer of the reference's motion encoder,
+//     cor = F.relu(self.convc1(corr))          core/update.py:70,77   (Conv2d(L*(2r+1), 64, 1))
+// so the L*(2r+1)-channel lookup result never goes to global memory.
+//
+// One CTA = 128 pixels = one UMMA M tile.  512 threads gather exactly like lookup_fwd_vec_kernel
+// (4 lanes per pixel, one aligned 16-byte chunk per lane and level, neighbour exchange by shuffle),
+// but instead of an output tile they write the interpolated taps, rounded to tf32, straight into
+// the K-major SWIZZLE_128B operand layout of tcgen05 (A = [128 px x K], K = L*9 padded to 64).
+// The weights (B = [Cout x K]) are staged the same way, one thread issues K/8 tcgen05.mma
+// (kind::tf32, fp32 accumulate in TMEM), and the epilogue reads TMEM with lane == pixel: for a
+// fixed output channel the 32 lanes of a warp hold 32 consecutive pixels, i.e. one 128-byte line
+// of the channel-major output -- the accumulator layout does the transpose.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace smoe {
+
+constexpr int kFcPx = 128;                 // pixels per CTA == UMMA M
+constexpr int kFcThreads = 4 * kFcPx;      // 4 lanes per pixel
+constexpr int kFcKPad = 64;                // K padded to two 32-element swizzle atoms
+constexpr int kFcABytes = 2 * kFcPx * 128;
+constexpr int kFcMaxCout = 256;
+
+__device__ __forceinline__ uint32_t to_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return r;
+}
+// byte offset of element (row, k) in a K-major SWIZZLE_128B operand of `rows` rows: 32-element
+// (128-byte) atoms along K, rows 128 bytes apart, 16-byte pieces XORed with (row & 7)
+__device__ __forceinline__ uint32_t kmajor_off(int row, int k, int rows) {
+  const int atom = k >> 5, kk = k & 31;
+  return (uint32_t)(atom * rows * 128 + row * 128 + ((((kk >> 2) ^ (row & 7)) << 4) | ((kk & 3) << 2)));
+}
+__device__ __forceinline__ void tmem_ld_32x32_x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+        "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// VT: pyramid element type; LT: the type the unfused lookup would return (float for CorrBlock1D,
+// the volume dtype for CorrBlockFast1D -- its interpolation arithmetic is reproduced);
+// CT: output type of the convolution.
+template <typename VT, typename LT, typename CT, int NL, bool STREAM>
+__global__ void __launch_bounds__(kFcThreads)
+lookup_conv_kernel(PyrDev pyr, const float* __restrict__ coords, long long coords_bstride,
+                   float coord_scale, const float* __restrict__ weight, const float* __restrict__ bias,
+                   int cout, int relu, uint32_t tmem_cols, CT* __restrict__ out, int HW, CoordUpd upd) {
+  constexpr int R = 4;
+  constexpr int RD = 2 * R + 1;
+  constexpr int K = NL * RD;                          // input channels of the convolution
+  constexpr int KMMA = (K + 7) / 8 * 8;               // K covered by the MMAs (zero padded)
+  constexpr int EPL = Vec16<VT>::N;
+  constexpr int LOG_EPL = (EPL == 4) ? 2 : 3;
+  constexpr int QMAX = (EPL - 1 + 2 * R + 1) >> LOG_EPL;
+  static_assert(KMMA <= kFcKPad, "K must fit the padded operand");
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ uint32_t s_tmem;
+  __shared__ float s_bias[kFcMaxCout];
+  const uint32_t sA = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;    // swizzle atoms: 1 KiB aligned
+  const uint32_t sB = sA + kFcABytes;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int p = tid >> 2, q = tid & 3;
+  const int b = blockIdx.y;
+  const int hw0 = blockIdx.x * kFcPx;
+  const int hw = hw0 + p;
+  const bool valid = hw < HW;
+
+  if (warp == 0) {
+    ptx::tmem_alloc(ptx::smem_u32(&s_tmem), tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  if (tid == 32) {
+    ptx::mbar_init(ptx::smem_u32(&s_bar), 1);
+    ptx::fence_barrier_init();
+  }
+  pdl_wait();
+  // ---- gather: issue the window loads of all levels first
+  const float x0 = valid ? fetch_coord(coords, coords_bstride, upd, b, hw, q == 0) * coord_scale : 0.f;
+  const long long row = (long long)b * HW + hw;
+  float v[NL][EPL];
+  float dxs[NL];
+  int shift[NL];
+  float lscale = 1.0f;
+#pragma unroll
+  for (int l = 0; l < NL; ++l) {
+    int base;
+    split_coord(x0 * lscale, R, base, dxs[l]);
+    lscale *= 0.5f;
+    const int s = base & (EPL - 1);
+    const int ci = (base >> LOG_EPL) + q;
+    shift[l] = s;
+    const int width = pyr.width[l];
+    const unsigned nchunks = (unsigned)(width + EPL - 1) >> LOG_EPL;
+    const bool need = valid && (q < QMAX || (q == QMAX && s + 2 * R + 1 >= QMAX * EPL)) &&
+                      (unsigned)ci < nchunks;
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) v[l][j] = 0.f;
+    if (need) {
+      const VT* src = static_cast<const VT*>(pyr.ptr[l]) + row * pyr.pitch[l] + (long long)ci * EPL;
+      Vec16<VT>::template load<STREAM>(src, v[l]);
+      if (__builtin_expect((ci + 1) * EPL > width, 0)) {
+#pragma unroll
+        for (int j = 0; j < EPL; ++j)
+          if (ci * EPL + j >= width) v[l][j] = 0.f;
+      }
+    }
+  }
+  // ---- weights -> B operand (tf32, zero padded to 64 columns) while the gathers are in flight
+  for (int idx = tid; idx < cout * (kFcKPad / 4); idx += kFcThreads) {
+    const int n = idx / (kFcKPad / 4), piece = idx % (kFcKPad / 4);
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = piece * 4 + j;
+      w[j] = k < K ? to_tf32(__ldg(weight + (long long)n * K + k)) : 0u;
+    }
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sB + kmajor_off(n, piece * 4, cout)),
+                 "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
+                 : "memory");
+  }
+  if (tid < cout) s_bias[tid] = bias != nullptr ? __ldg(bias + tid) : 0.f;
+  // zero the K padding the MMAs read (columns K .. KMMA-1 of every pixel row)
+  if (q == 0) {
+#pragma unroll
+    for (int k = K; k < KMMA; ++k)
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(sA + kmajor_off(p, k, kFcPx)), "r"(0u) : "memory");
+  }
+  // ---- interpolate; tap k of level l sits at window position shift+k of the 4-chunk span
+#pragma unroll
+  for (int l = 0; l < NL; ++l) {
+    const float nxt = __shfl_down_sync(0xffffffffu, v[l][0], 1);
+    float e[EPL];
+    LerpChunk<LT, EPL>::run(v[l], nxt, dxs[l], e);
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) {
+      const int k = q * EPL + i - shift[l];
+      if (k >= 0 && k < RD)
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(sA + kmajor_off(p, l * RD + k, kFcPx)),
+                     "r"(to_tf32(e[i]))
+                     : "memory");
+    }
+  }
+  pdl_launch_dependents();
+  ptx::fence_proxy_async_smem();          // generic-proxy operand writes -> tensor-core (async) proxy
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem = s_tmem;
+  if (tid == 0) {
+    // c_format f32 | tf32 x tf32 | A, B K-major | N | M
+    const uint32_t idesc = (1u << 4) | (ptx::kFmtTF32 << 7) | (ptx::kFmtTF32 << 10) |
+                           (((uint32_t)cout >> 3) << 17) | ((uint32_t)(kFcPx >> 4) << 24);
+#pragma unroll
+    for (int ks = 0; ks < KMMA / 8; ++ks) {
+      const int atom = (ks * 8) >> 5, kin = (ks * 8) & 31;
+      // K-major SW128: 8-row groups 1 KiB apart (SBO), 32 bytes per UMMA_K inside the 128-byte row
+      const uint64_t adesc = ptx::make_smem_desc(sA + atom * kFcPx * 128 + kin * 4, 16, 1024, ptx::kLayoutSwizzle128B);
+      const uint64_t bdesc = ptx::make_smem_desc(sB + atom * cout * 128 + kin * 4, 16, 1024, ptx::kLayoutSwizzle128B);
+      ptx::mma_tf32(tmem, adesc, bdesc, idesc, ks != 0 ? 1u : 0u);
+    }
+    ptx::tc_commit(ptx::smem_u32(&s_bar));
+  }
+  ptx::mbar_wait(ptx::smem_u32(&s_bar), 0);
+  ptx::tc_fence_after_sync();
+  // ---- epilogue: TMEM lane == pixel; the 4 warps of a lane quadrant split the output channels
+  const int quad = warp & 3, part = warp >> 2;
+  const int px = quad * 32 + lane;
+  const bool store = hw0 + px < HW;
+  CT* obase = out + (long long)b * cout * HW + hw0 + px;
+  for (int c0 = part * 16; c0 < cout; c0 += 64) {
+    uint32_t acc[16];
+    tmem_ld_32x32_x16(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, acc);
+    ptx::tmem_ld_wait();
+    if (store) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float r = __uint_as_float(acc[j]) + s_bias[c0 + j];
+        if (relu) r = fmaxf(r, 0.f);
+        obase[(long long)(c0 + j) * HW] = from_float<CT>(r);
+      }
+    }
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc(tmem, tmem_cols);
+  }
+}
+
+bool pyramid_vec_ok(const smoe_pyramid_t* p);   // lookup.cu
+
+template <typename VT, typename LT, typename CT>
+static int launch_lookup_conv(const smoe_pyramid_t* pyr, const float* coords, long long cbs, float cs,
+                              const float* weight, const float* bias, int cout, int relu, void* out,
+                              cudaStream_t st, const CoordUpd& upd) {
+  const PyrDev d = to_dev(pyr);
+  const int HW = pyr->H * pyr->W1;
+  const size_t smem = (size_t)kFcABytes + (size_t)cout * 256 + 1024;
+  uint32_t cols = 32;
+  while ((int)cols < cout) cols <<= 1;
+  const bool big = (long long)pyr->B * HW * d.pitch[0] * (long long)sizeof(VT) > (96ll << 20);
+  dim3 grid((HW + kFcPx - 1) / kFcPx, pyr->B);
+#define SMOE_FC_LAUNCH(NLV, STREAMV)                                                              \
+  do {                                                                                            \
+    auto kern = lookup_conv_kernel<VT, LT, CT, NLV, STREAMV>;                                     \
+    SMOE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    SMOE_CUDA_OK(launch_kernel(kern, grid, dim3(kFcThreads), smem, st, d, coords, cbs, cs, weight, \
+                               bias, cout, relu, cols, static_cast<CT*>(out), HW, upd));          \
+  } while (0)
+#define SMOE_FC_LEVELS(STREAMV)                                                                   \
+  switch (pyr->num_levels) {                                                                      \
+    case 1: SMOE_FC_LAUNCH(1, STREAMV); break;                                                    \
+    case 2: SMOE_FC_LAUNCH(2, STREAMV); break;                                                    \
+    case 3: SMOE_FC_LAUNCH(3, STREAMV); break;                                                    \
+    default: SMOE_FC_LAUNCH(4, STREAMV); break;                                                   \
+  }
+  if (big) { SMOE_FC_LEVELS(true) } else { SMOE_FC_LEVELS(false) }
+#undef SMOE_FC_LEVELS
+#undef SMOE_FC_LAUNCH
+  return check_launch("lookup_conv_kernel");
+}
+
+}  // namespace smoe
+
+extern "C" int smoe_corr_lookup_conv1x1(const smoe_pyramid_t* pyr, const float* coords,
+                                        int64_t coords_batch_stride, float coord_scale, int radius,
+                                        int lookup_dtype, const float* weight, const float* bias,
+                                        int cout, int relu, void* out, int out_dtype,
+                                        smoe_stream_t stream) {
+  using namespace smoe;
+  if (int rc = validate_pyramid(pyr, "lookup_conv1x1")) return rc;
+  SMOE_REQUIRE(dtype_ok(lookup_dtype) && dtype_ok(out_dtype), SMOE_ERR_INVALID_ARG,
+               "lookup_conv1x1: unknown dtype (lookup %d, out %d)", lookup_dtype, out_dtype);
+  SMOE_REQUIRE(!(pyr->dtype == SMOE_DTYPE_F32 && lookup_dtype == SMOE_DTYPE_F16), SMOE_ERR_UNSUPPORTED,
+               "lookup_conv1x1: fp16 lookup arithmetic on an fp32 pyramid is not part of the reference API");
+  SMOE_REQUIRE(radius == 4, SMOE_ERR_UNSUPPORTED,
+               "lookup_conv1x1: radius %d (the fused kernel is built for radius 4; run lookup + conv)", radius);
+  SMOE_REQUIRE(cout >= 16 && cout <= kFcMaxCout && cout % 16 == 0, SMOE_ERR_UNSUPPORTED,
+               "lookup_conv1x1: %d output channels (need a multiple of 16 in [16,%d])", cout, kFcMaxCout);
+  SMOE_REQUIRE(pyramid_vec_ok(pyr), SMOE_ERR_UNSUPPORTED,
+               "lookup_conv1x1: pyramid levels must be 16-byte aligned with 16-byte-multiple pitches");
+  const long long HW = (long long)pyr->H * pyr->W1;
+  if (pyr->B == 0 || HW == 0) return SMOE_OK;
+  SMOE_REQUIRE(coords && out && weight, SMOE_ERR_INVALID_ARG, "lookup_conv1x1: NULL coords/weight/out pointer");
+  SMOE_REQUIRE(coords_batch_stride >= HW, SMOE_ERR_INVALID_ARG,
+               "lookup_conv1x1: coords batch stride %lld < H*W1 %lld", (long long)coords_batch_stride, HW);
+  SMOE_REQUIRE(pyr->B <= 65535 && HW < (1ll << 31), SMOE_ERR_UNSUPPORTED, "lookup_conv1x1: batch/plane too large");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const CoordUpd none = {nullptr, nullptr, nullptr, nullptr, 0};
+  const bool f16v = pyr->dtype == SMOE_DTYPE_F16, f16l = lookup_dtype == SMOE_DTYPE_F16,
+             f16o = out_dtype == SMOE_DTYPE_F16;
+#define SMOE_FC_GO(VT, LT)                                                                           \
+  return f16o ? launch_lookup_conv<VT, LT, __half>(pyr, coords, coords_batch_stride, coord_scale,     \
+                                                   weight, bias, cout, relu, out, st, none)           \
+              : launch_lookup_conv<VT, LT, float>(pyr, coords, coords_batch_stride, coord_scale,      \
+                                                  weight, bias, cout, relu, out, st, none)
+  if (!f16v) { SMOE_FC_GO(float, float); }
+  if (f16l) { SMOE_FC_GO(__half, __half); }
+  SMOE_FC_GO(__half, float);
+#undef SMOE_FC_GO
+}

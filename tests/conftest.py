@@ -18,8 +18,22 @@ def pytest_configure(config):
 
 
 def golden_names():
-    return sorted(os.path.splitext(os.path.basename(p))[0]
-                  for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    """Correlation-path fixtures (the convc1_* files hold the consumer layer of some of them)."""
+    return sorted(n for n in (os.path.splitext(os.path.basename(p))[0]
+                              for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+                  if not n.startswith("convc1_"))
+
+
+def convc1_names():
+    return sorted(os.path.splitext(os.path.basename(p))[0][len("convc1_"):]
+                  for p in glob.glob(os.path.join(GOLDEN_DIR, "convc1_*.npz")))
+
+
+def load_convc1(name):
+    """weight (64, L*(2r+1)), bias (64,), cor (T,B,64,H,W1) = relu(convc1(out[t])) of fixture `name`
+    (reference core/update.py:70,77; tests/golden/make_golden.py)."""
+    with np.load(os.path.join(GOLDEN_DIR, "convc1_" + name + ".npz")) as z:
+        return {k: z[k] for k in z.files}
 
 
 def load_golden(name):

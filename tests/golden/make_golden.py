@@ -19,6 +19,11 @@ Stored per case:
   gout            (T,B,L*(2r+1),H,W1) upstream gradient used for backward
   glvl{i}         d(sum_t <out_t,gout_t>)/d(level i)  (B,H,W1,W2_i)        autograd of grid_sample
   df1,df2         gradients w.r.t. the feature maps                        autograd of the whole path
+
+convc1_<case>.npz (the consumer of the lookup), from the reference's
+``core/update.py`` BasicMotionEncoder with seeded random weights:
+  weight,bias     convc1 parameters (64, L*(2r+1)), (64,)                  core/update.py:70
+  cor             (T,B,64,H,W1) = F.relu(convc1(out[t]))                   core/update.py:77
 """
 import os
 import sys
@@ -115,8 +120,29 @@ def run_case(name, spec):
     print(f"{name}: wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB)")
 
 
+def run_convc1_case(name, spec):
+    """Reference motion-encoder first layer on the stored lookup outputs of `name`."""
+    from types import SimpleNamespace
+    from core.update import BasicMotionEncoder
+    B, C, H, W1, W2, L, r, T, _ = spec
+    out = np.load(os.path.join(HERE, f"{name}.npz"))["out"]
+    torch.manual_seed(1000 + sum(map(ord, name)))
+    enc = BasicMotionEncoder(SimpleNamespace(corr_levels=L, corr_radius=r))
+    with torch.no_grad():
+        # default Conv2d init gives |w| <= 1/6; scale up so that the ReLU clips about half
+        enc.convc1.weight.mul_(3.0)
+        cor = np.stack([torch.relu(enc.convc1(torch.from_numpy(out[t]))).numpy() for t in range(T)])
+    path = os.path.join(HERE, f"convc1_{name}.npz")
+    np.savez_compressed(path, weight=enc.convc1.weight.detach().numpy().reshape(64, -1),
+                        bias=enc.convc1.bias.detach().numpy(), cor=cor)
+    print(f"convc1_{name}: wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB)")
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     torch.set_num_threads(4)
-    for n, s in CASES.items():
-        run_case(n, s)
+    if "--convc1-only" not in sys.argv:
+        for n, s in CASES.items():
+            run_case(n, s)
+    for n in ("odd37", "c256_w40", "fp16_valued_w64"):
+        run_convc1_case(n, CASES[n])

@@ -112,3 +112,17 @@ def test_nonfinite_coords_give_zero(oracle):
     for fn in (oracle.numpy_lookup, oracle.c_lookup):
         out = fn([vol], coords, 2)
         assert np.all(out == 0)
+
+
+@pytest.mark.parametrize("name", __import__("conftest").convc1_names())
+def test_oracle_conv1x1_matches_reference_motion_encoder(oracle, name):
+    """The restated consumer layer (relu(convc1(corr)), core/update.py:70,77) against the
+    reference's own BasicMotionEncoder output stored by make_golden.py."""
+    from conftest import load_convc1
+    g = load_golden(name)
+    c = load_convc1(name)
+    assert c["weight"].shape == (64, g["dims"]["L"] * (2 * g["dims"]["r"] + 1))
+    for t in range(g["dims"]["T"]):
+        got = oracle.numpy_conv1x1(g["out"][t], c["weight"], c["bias"], relu=True)
+        assert rel_max(got, c["cor"][t]) < 2e-6
+        assert (c["cor"][t] == 0).mean() > 0.2          # the ReLU does clip in these fixtures
