@@ -75,7 +75,7 @@ lookup_conv_kernel(PyrDev pyr, const float* __restrict__ coords, long long coord
   const int hw = hw0 + p;
   const bool valid = hw < HW;
 
-  if (warp == 0) {
+  if (warp == 0) {      // (allocating after the gathers are issued measured slower: 9.8 vs 8.8 us)
     ptx::tmem_alloc(ptx::smem_u32(&s_tmem), tmem_cols);
     ptx::tmem_relinquish();
   }
