@@ -25,7 +25,8 @@
  *
  * Data layout
  * -----------
- * Feature maps are NCHW contiguous, (B,C,H,W), fp32 or fp16 (core/extractor.py:603-609).
+ * Feature maps are NCHW contiguous, (B,C,H,W), fp32 or fp16 (core/extractor.py:603-609); or, with
+ * SMOE_BUILD_CHANNELS_LAST, the same logical tensor stored (B,H,W,C).
  * Coordinates are (B,coords_ch,H,W1) fp32; only channel 0 (x) is read (core/corr.py:129,
  * :47).  Lookup outputs are (B, L*(2r+1), H, W1) contiguous, channel = level*(2r+1)+tap
  * (core/corr.py:143-146).
@@ -63,6 +64,13 @@ extern "C" {
 #define SMOE_BUILD_TF32_TRUNCATE 1 /* fp32 inputs: load with a FLOAT32 tensor map so that tcgen05
                                       kind::tf32 truncates the low 13 mantissa bits itself; default
                                       (0) is a TFLOAT32 tensor map (TMA converts on the way in)  */
+
+#define SMOE_BUILD_CHANNELS_LAST 2 /* feature maps are channels-last: (B,H,W,C) in memory (what a
+                                      torch NCHW-shaped tensor in memory_format=channels_last is, and
+                                      what a channels-last producer convolution emits; SURVEY.md 8f
+                                      row f4).  Both operands are then K-major for the tensor cores.
+                                      Needs C*sizeof(T) % 16 == 0; no constraint on W1/W2 and no
+                                      workspace.                                                   */
 
 /* smoe_corr_lookup_bwd modes */
 #define SMOE_BWD_OVERWRITE 0     /* write every element of the gradient (zeros outside the taps):

@@ -17,6 +17,7 @@ ABI_VERSION = 1
 OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_CUDA = 0, 1, 2, 3
 DTYPE_F32, DTYPE_F16 = 0, 1
 BUILD_TF32_TRUNCATE = 1
+BUILD_CHANNELS_LAST = 2
 BWD_OVERWRITE, BWD_ACCUMULATE = 0, 1
 MAX_BATCHED_ITERS = 48
 

@@ -123,12 +123,42 @@ class FusedPyramid:
         return v.view(self.B, self.H, self.W1, self.widths[i])
 
 
+def _is_channels_last(t: torch.Tensor) -> bool:
+    """(B,C,H,W)-shaped tensor stored (B,H,W,C) -- and not also NCHW-contiguous (C == 1 etc.)."""
+    return (t.dim() == 4 and not t.is_contiguous()
+            and t.is_contiguous(memory_format=torch.channels_last))
+
+
+def _layout_for_build(fmap1: torch.Tensor, fmap2: torch.Tensor):
+    """Pick the memory layout the build kernel reads in place.
+
+    Feature maps that arrive channels-last -- what cuDNN emits for a model run in
+    ``memory_format=torch.channels_last``, e.g. the decoder's last 1x1 convolution
+    (core/extractor.py:565-570) -- are consumed as they are (K-major operands, flag
+    SMOE_BUILD_CHANNELS_LAST) when C*itemsize is a multiple of 16; everything else is made NCHW
+    contiguous, as the reference's einsum would do internally."""
+    if (_is_channels_last(fmap1) or _is_channels_last(fmap2)) and \
+            (fmap1.shape[1] * fmap1.element_size()) % 16 == 0:
+        f1 = fmap1.contiguous(memory_format=torch.channels_last)
+        f2 = fmap2.contiguous(memory_format=torch.channels_last)
+        if f1.data_ptr() % 16 == 0 and f2.data_ptr() % 16 == 0:
+            return f1, f2
+    return fmap1.contiguous(), fmap2.contiguous()
+
+
 def _build_into(pyr: FusedPyramid, fmap1: torch.Tensor, fmap2: torch.Tensor, flags: int = 0) -> None:
     B, C, H, W1 = fmap1.shape
     W2 = fmap2.shape[3]
     L = _lib.lib()
     code = _DTYPE_CODE[fmap1.dtype]
-    ws_bytes = L.smoe_corr_build_workspace_bytes(B, C, H, W1, W2, code)
+    if _is_channels_last(fmap1):
+        if not _is_channels_last(fmap2):
+            raise RuntimeError("fmap1 and fmap2 must share one memory layout")
+        flags |= _lib.BUILD_CHANNELS_LAST
+    elif not (fmap1.is_contiguous() and fmap2.is_contiguous()):
+        raise RuntimeError("feature maps must be contiguous (NCHW or channels-last)")
+    ws_bytes = 0 if flags & _lib.BUILD_CHANNELS_LAST else \
+        L.smoe_corr_build_workspace_bytes(B, C, H, W1, W2, code)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=fmap1.device) if ws_bytes else None
     with _on_device(fmap1.device):
         rc = L.smoe_corr_build(fmap1.data_ptr(), fmap2.data_ptr(), code, B, C, H, W1, W2, pyr.ref,
@@ -348,8 +378,7 @@ class _CorrBlockBase:
             fmap1, fmap2 = fmap1.float(), fmap2.float()
         self.num_levels = num_levels
         self.radius = radius
-        fmap1 = fmap1.contiguous()
-        fmap2 = fmap2.contiguous()
+        fmap1, fmap2 = _layout_for_build(fmap1, fmap2)
         st = _State()
         pyr_dtype = fmap1.dtype
         if self._float_output and fmap1.dtype == torch.float32 and _default_volume_dtype is not None:
@@ -481,10 +510,10 @@ class _CorrVolumeFn(torch.autograd.Function):
     def forward(ctx, fmap1, fmap2):
         _require_cuda(fmap1, "fmap1")
         _require_cuda(fmap2, "fmap2")
-        f1 = fmap1.contiguous()
-        f2 = fmap2.contiguous()
+        f1, f2 = fmap1, fmap2
         if f1.dtype not in _DTYPE_CODE:
             f1, f2 = f1.float(), f2.float()
+        f1, f2 = _layout_for_build(f1, f2)
         pyr = FusedPyramid(f1.shape[0], f1.shape[2], f1.shape[3], f2.shape[3], 1, f1.dtype, f1.device)
         _build_into(pyr, f1, f2)
         ctx.save_for_backward(f1, f2)

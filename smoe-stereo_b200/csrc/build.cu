@@ -89,6 +89,7 @@ struct BuildDims {
   int stages;                // operand ring: depth and bytes per stage (A 16 KiB + the B slabs
   int stage_bytes;           // one N tile needs), sized to fill shared memory
   int pair;                  // CTA-pair kernel (MT counts 256-row tiles)
+  int kmajor;                // channels-last feature maps (SMOE_BUILD_CHANNELS_LAST)
   int debug;                 // probe builds only (kProbes)
 };
 
@@ -312,7 +313,13 @@ __device__ __forceinline__ void store_staged_tile(uint32_t tile, int d, OT* __re
 // fetched from L2 once per 256 output rows instead of once per 128.  Rank 0 (the leader) owns
 // the `full` and `accumulator empty` barriers and issues the MMAs; both CTAs run their own
 // producer and epilogue; `empty` / `accumulator full` arrive in both CTAs by multicast commit.
-template <typename IT, typename OT, bool kPair>
+//
+// kKMajor: the feature maps are channels-last, (B,H,W,C) in memory, so both operands are K-major
+// (the contraction axis C is contiguous): the canonical UMMA layout.  One TMA box {128 bytes of C,
+// rows of W} per operand and stage lands as 8-row SWIZZLE_128B atoms; there is no 16-byte rule on
+// W any more (the W stride is C*sizeof(T)), so odd widths need no pitch-padding pre-pass
+// (the layout a channels-last producer convolution emits).
+template <typename IT, typename OT, bool kPair, bool kKMajor>
 __global__ void __launch_bounds__(kBuildThreads, 1)
 corr_build_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const PyrDev out, const int num_levels, const BuildDims dims,
@@ -324,6 +331,8 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   constexpr uint32_t kKStepBytes = Cfg::kUmmaK * 128;        // smem advance per MMA along K
   static_assert(kSlabsA * kSlabBytes == kStageABytes, "A stage size");
   static_assert((kBlockN / Cfg::kSlab) * kSlabBytes == kStageBBytes, "B stage size");
+  static_assert(!(kPair && kKMajor), "the CTA-pair kernel exists for NCHW operands only");
+  static_assert(Cfg::kKT * sizeof(IT) == 128 && Cfg::kUmmaK * sizeof(IT) == 32, "K-major row / K step");
 
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t s_full[kMaxStages], s_empty[kMaxStages], s_tfull[2], s_tempty[2];
@@ -390,7 +399,10 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         // pair: this CTA's half of the N tile (whole slabs), leader expects both CTAs' bytes
         const int slabs_b = kPair ? (n_valid + 2 * Cfg::kSlab - 1) / (2 * Cfg::kSlab)
                                   : (n_valid + Cfg::kSlab - 1) / Cfg::kSlab;
-        const uint32_t tx_bytes = (uint32_t)(kSlabsA + slabs_b) * kSlabBytes * (kPair ? 2u : 1u);
+        // K-major: one box of kBlockM rows (A) and one of BN rows (B), 128 bytes of C each; rows
+        // beyond W are zero-filled by TMA but count in the transaction bytes
+        const uint32_t tx_bytes = kKMajor ? (uint32_t)(kBlockM + dims.BN) * 128u
+                                          : (uint32_t)(kSlabsA + slabs_b) * kSlabBytes * (kPair ? 2u : 1u);
         const int a_row0 = (kPair ? mt * 2 + (int)rank : mt) * kBlockM;
         const int b_col0 = nt * dims.BN + (kPair ? (int)rank * slabs_b * Cfg::kSlab : 0);
         for (int ks = 0; ks < num_k; ++ks) {
@@ -405,7 +417,10 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           const uint32_t full = kPair ? ptx::map_to_cta(full_local, 0) : full_local;
           const uint32_t sa = smem_base + stage * dims.stage_bytes;
           const uint32_t sb = sa + kStageABytes;
-          if (kPair) {
+          if (kKMajor) {
+            ptx::tma_load_4d(sa, &tmap_a, full, ks * Cfg::kKT, a_row0, h, b);
+            ptx::tma_load_4d(sb, &tmap_b, full, ks * Cfg::kKT, b_col0, h, b);
+          } else if (kPair) {
 #pragma unroll
             for (int j = 0; j < kSlabsA; ++j)
               ptx::tma_load_4d_pair(sa + j * kSlabBytes, &tmap_a, full, a_row0 + j * Cfg::kSlab, h,
@@ -441,7 +456,8 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const uint32_t n_mma =
             kPair ? (uint32_t)((n_valid + 2 * Cfg::kSlab - 1) / (2 * Cfg::kSlab) * (2 * Cfg::kSlab))
                   : (uint32_t)((n_valid + 15) & ~15);
-        const uint32_t idesc = ptx::make_idesc_mn_major(Cfg::kFmt, kPair ? 2 * kBlockM : kBlockM, n_mma);
+        const uint32_t idesc = kKMajor ? ptx::make_idesc_k_major(Cfg::kFmt, kBlockM, n_mma)
+                                       : ptx::make_idesc_mn_major(Cfg::kFmt, kPair ? 2 * kBlockM : kBlockM, n_mma);
         if (kPair) ptx::mbar_wait_cluster(ptx::smem_u32(&s_tempty[buf]), bphase ^ 1u);
         else ptx::mbar_wait(ptx::smem_u32(&s_tempty[buf]), bphase ^ 1u);
         ptx::tc_fence_after_sync();
@@ -456,10 +472,14 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll
           for (int kk = 0; kk < kKSteps; ++kk) {
             if (kProbes && (dims.debug & 4)) break;
+            // MN-major: slabs kSlabBytes apart (LBO), one UMMA_K = kKStepBytes further down.
+            // K-major SWIZZLE_128B: 8-row atoms of 1 KiB (SBO), 32 bytes per UMMA_K inside the row.
             const uint64_t adesc =
-                ptx::make_smem_desc(sa + kk * kKStepBytes, kSlabBytes, Cfg::kSBO, Cfg::kLayout);
+                kKMajor ? ptx::make_smem_desc(sa + kk * 32, 16, 1024, ptx::kLayoutSwizzle128B)
+                        : ptx::make_smem_desc(sa + kk * kKStepBytes, kSlabBytes, Cfg::kSBO, Cfg::kLayout);
             const uint64_t bdesc =
-                ptx::make_smem_desc(sb + kk * kKStepBytes, kSlabBytes, Cfg::kSBO, Cfg::kLayout);
+                kKMajor ? ptx::make_smem_desc(sb + kk * 32, 16, 1024, ptx::kLayoutSwizzle128B)
+                        : ptx::make_smem_desc(sb + kk * kKStepBytes, kSlabBytes, Cfg::kSBO, Cfg::kLayout);
             if (kPair)
               ptx::mma_pair<sizeof(IT) == 4>(d_tmem, adesc, bdesc, idesc, (ks | kk) != 0 ? 1u : 0u);
             else if (sizeof(IT) == 4)
@@ -629,11 +649,34 @@ static int make_fmap_tmap(CUtensorMap* out, const void* base, int dtype, bool tf
   return SMOE_OK;
 }
 
+// 4-D map over a channels-last feature map (memory (B,H,W,C); dims C,W,H,B), box = 128 bytes of C
+// x `rows` pixels of one image row.
+static int make_fmap_tmap_cl(CUtensorMap* out, const void* base, int dtype, bool tf32_round, int B, int C,
+                             int H, int W, int rows) {
+  EncodeTiledFn enc = encode_fn();
+  SMOE_REQUIRE(enc != nullptr, SMOE_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  const int es = dtype_size(dtype);
+  const cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  const cuuint64_t gstr[3] = {(cuuint64_t)C * es, (cuuint64_t)W * C * es, (cuuint64_t)H * W * C * es};
+  const cuuint32_t box[4] = {(cuuint32_t)(128 / es), (cuuint32_t)rows, 1u, 1u};
+  const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  const CUtensorMapDataType dt =
+      dtype == SMOE_DTYPE_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                              : (tf32_round ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
+  const CUresult r = enc(out, dt, 4, const_cast<void*>(base), gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SMOE_REQUIRE(r == CUDA_SUCCESS, SMOE_ERR_CUDA,
+               "cuTensorMapEncodeTiled (channels-last) failed with CUresult %d (W=%d H=%d C=%d B=%d rows=%d)",
+               (int)r, W, H, C, B, rows);
+  return SMOE_OK;
+}
+
 static thread_local long long* g_timeline = nullptr;   // smoe_corr_debug_set_timeline
 
-template <typename IT, typename OT, bool kPair>
+template <typename IT, typename OT, bool kPair, bool kKMajor = false>
 static int launch_build_impl(const CUtensorMap& ta, const CUtensorMap& tb, const PyrDev& out, int num_levels, const BuildDims& dims, cudaStream_t st) {
-  auto kern = corr_build_kernel<IT, OT, kPair>;
+  auto kern = corr_build_kernel<IT, OT, kPair, kKMajor>;
   const size_t smem_bytes = (size_t)dims.stages * dims.stage_bytes + kBuildSmemFixed;
   SMOE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   int dev = 0, sms = 0;
@@ -648,6 +691,7 @@ static int launch_build_impl(const CUtensorMap& ta, const CUtensorMap& tb, const
 }
 template <typename IT, typename OT>
 static int launch_build(const CUtensorMap& ta, const CUtensorMap& tb, const PyrDev& out, int num_levels, const BuildDims& dims, cudaStream_t st) {
+  if (dims.kmajor) return launch_build_impl<IT, OT, false, true>(ta, tb, out, num_levels, dims, st);
   return dims.pair ? launch_build_impl<IT, OT, true>(ta, tb, out, num_levels, dims, st)
                    : launch_build_impl<IT, OT, false>(ta, tb, out, num_levels, dims, st);
 }
@@ -705,8 +749,12 @@ int smoe_corr_build(const void* fmap1, const void* fmap2, int in_dtype, int B, i
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int es = dtype_size(in_dtype);
 
-  // pitch-padded staging for W that violates TMA's 16-byte stride rule
-  const int p1 = padded_width(W1, es), p2 = padded_width(W2, es);
+  const bool kmajor = (flags & SMOE_BUILD_CHANNELS_LAST) != 0;
+  SMOE_REQUIRE(!kmajor || ((long long)C * es) % 16 == 0, SMOE_ERR_UNSUPPORTED,
+               "build: channels-last feature maps need C*sizeof(T) %% 16 == 0 (C=%d)", C);
+
+  // pitch-padded staging for W that violates TMA's 16-byte stride rule (NCHW operands only)
+  const int p1 = kmajor ? W1 : padded_width(W1, es), p2 = kmajor ? W2 : padded_width(W2, es);
   const void* a_base = fmap1;
   const void* b_base = fmap2;
   if (p1 != W1 || p2 != W2) {
@@ -738,15 +786,13 @@ int smoe_corr_build(const void* fmap1, const void* fmap2, int in_dtype, int B, i
   }
 
   const bool tf32_round = (flags & SMOE_BUILD_TF32_TRUNCATE) == 0;
-  CUtensorMap ta, tb;
-  if (int rc = make_fmap_tmap(&ta, a_base, in_dtype, tf32_round, B, C, H, W1, p1)) return rc;
-  if (int rc = make_fmap_tmap(&tb, b_base, in_dtype, tf32_round, B, C, H, W2, p2)) return rc;
 
   BuildDims dims;
   dims.W1 = W1; dims.W2 = W2; dims.C = C; dims.H = H; dims.BH = B * H;
+  dims.kmajor = kmajor ? 1 : 0;
   {
     const char* e = getenv("SMOE_CORR_BUILD_PAIR");
-    dims.pair = e ? atoi(e) : 0;
+    dims.pair = (e && !kmajor) ? atoi(e) : 0;
   }
   dims.MT = (W1 + (dims.pair ? 2 : 1) * kBlockM - 1) / ((dims.pair ? 2 : 1) * kBlockM);
   dims.NT = (W2 + kBlockN - 1) / kBlockN;
@@ -770,6 +816,14 @@ int smoe_corr_build(const void* fmap1, const void* fmap2, int in_dtype, int B, i
     if (dims.stages > kMaxStages) dims.stages = kMaxStages;
     const char* e = getenv("SMOE_CORR_BUILD_STAGES");      // experiment switch
     if (e && atoi(e) >= 2 && atoi(e) < dims.stages) dims.stages = atoi(e);
+  }
+  CUtensorMap ta, tb;
+  if (kmajor) {
+    if (int rc = make_fmap_tmap_cl(&ta, a_base, in_dtype, tf32_round, B, C, H, W1, kBlockM)) return rc;
+    if (int rc = make_fmap_tmap_cl(&tb, b_base, in_dtype, tf32_round, B, C, H, W2, dims.BN)) return rc;
+  } else {
+    if (int rc = make_fmap_tmap(&ta, a_base, in_dtype, tf32_round, B, C, H, W1, p1)) return rc;
+    if (int rc = make_fmap_tmap(&tb, b_base, in_dtype, tf32_round, B, C, H, W2, p2)) return rc;
   }
   dims.denom = denom;
   dims.rcp = 1.0f / denom;

@@ -274,5 +274,10 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_mn_major(uint32_t fmt, u
          ((M >> 4) << 24);
 }
 
+// Same with both operands K-major (contraction axis contiguous in shared memory).
+__host__ __device__ __forceinline__ uint32_t make_idesc_k_major(uint32_t fmt, uint32_t M, uint32_t N) {
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
 }  // namespace ptx
 }  // namespace smoe

@@ -189,3 +189,101 @@ def test_build_cta_pair_kernel_is_bit_identical(sb, monkeypatch, shape, dtype):
     got = cls(f1, f2, num_levels=4, radius=4).corr_pyramid
     for i, (a, b) in enumerate(zip(ref, got)):
         assert torch.equal(a, b), f"level {i} differs"
+
+
+# ------------------------------------------------------------------ channels-last (K-major) inputs
+@pytest.mark.parametrize("shape", [
+    (1, 256, 135, 240, 240),    # BASELINE config 1
+    (2, 256, 6, 184, 184),      # config 2 width: M tail of 56 rows
+    (1, 256, 4, 312, 312),      # config 3 width: 2 N tiles
+    (1, 256, 3, 750, 750),      # config 4 width: W%4 != 0 needs NO padding pass in this layout
+    (1, 100, 2, 72, 520),       # C tail inside the last K stage (zero-filled by TMA), W1 != W2
+    (2, 64, 4, 37, 52),         # narrow odd widths, boxes larger than the tensor
+    (1, 8, 2, 16, 24),          # a single partial K stage
+])
+def test_build_channels_last_vs_oracle_and_nchw(sb, oracle, shape):
+    """channels-last feature maps are read in place as K-major operands.
+    fp32: same tf32 products, same fp32 accumulation order over C as the NCHW path -> the two
+    layouts must agree (bit for bit in practice; 1e-6 asserted); both are held to the oracle at north_star's tolerance."""
+    from gpu_util import dev
+    B, C, H, W1, W2 = shape
+    rs = np.random.RandomState(B * 1000 + W1 + 7)
+    f1 = rs.standard_normal((B, C, H, W1)).astype(np.float32)
+    f2 = rs.standard_normal((B, C, H, W2)).astype(np.float32)
+    want = oracle.c_pyramid(oracle.c_corr_volume(f1, f2), 4)
+    t1, t2 = torch.from_numpy(f1).to(dev()), torch.from_numpy(f2).to(dev())
+    c1 = t1.contiguous(memory_format=torch.channels_last)
+    c2 = t2.contiguous(memory_format=torch.channels_last)
+    assert not c1.is_contiguous() and c1.stride(1) == 1
+    blk = sb.CorrBlock1D(c1, c2)
+    lv = _levels(blk)
+    ref = _levels(sb.CorrBlock1D(t1, t2))
+    for i in range(4):
+        e = rel_max(lv[i], want[i])
+        print(f"[build channels_last {shape}] level {i}: rel_max={e:.3e}")
+        assert e < VOL_TOL
+        print(f"   vs NCHW build: bit-identical={np.array_equal(lv[i], ref[i])} rel_max={rel_max(lv[i], ref[i]):.2e}")
+        assert rel_max(lv[i], ref[i]) < 1e-6
+    # mixed layouts: the NCHW map is converted, not misread
+    mixed = _levels(sb.CorrBlock1D(c1, t2))
+    np.testing.assert_array_equal(mixed[0], lv[0])
+
+
+@pytest.mark.parametrize("fast", [False, True])
+def test_build_channels_last_fp16(sb, fast):
+    """fp16 channels-last feature maps (the autocast producer format of row f4, half the input
+    bytes): kind::f16 K-major operands; same result as the NCHW fp16 build."""
+    from gpu_util import dev
+    g = torch.Generator(device="cpu").manual_seed(3)
+    f1 = torch.randn(2, 256, 5, 184, generator=g).half().to(dev())
+    f2 = torch.randn(2, 256, 5, 184, generator=g).half().to(dev())
+    cls = sb.CorrBlockFast1D if fast else sb.CorrBlock1D
+    a = cls(f1, f2)
+    b = cls(f1.contiguous(memory_format=torch.channels_last), f2.contiguous(memory_format=torch.channels_last))
+    assert a._state.pyr.dtype == b._state.pyr.dtype == torch.float16
+    for la, lb in zip(a.corr_pyramid, b.corr_pyramid):
+        print(f"[fp16 channels_last fast={fast}] bit-identical to NCHW: {torch.equal(la, lb)}")
+        assert rel_max(lb.float().cpu().numpy(), la.float().cpu().numpy()) < 1e-3
+    want = torch.einsum("bchw,bchv->bhwv", f1.float(), f2.float()) / 16.0
+    assert rel_max(b.corr_pyramid[0].squeeze(3).float().cpu().numpy(), want.cpu().numpy()) < VOL_TOL
+
+
+def test_build_channels_last_c_abi_rejects_unaligned_channels(sb):
+    """C*sizeof(T) % 16 != 0 cannot be a TMA stride: the C ABI says so, the class converts to NCHW."""
+    from gpu_util import dev
+    from smoe_stereo_b200 import _lib
+    from smoe_stereo_b200.corr import _build_into
+    g = torch.Generator(device="cpu").manual_seed(4)
+    f1 = torch.randn(1, 6, 3, 40, generator=g).to(dev())
+    f2 = torch.randn(1, 6, 3, 40, generator=g).to(dev())
+    c1 = f1.contiguous(memory_format=torch.channels_last)
+    c2 = f2.contiguous(memory_format=torch.channels_last)
+    pyr = sb.FusedPyramid(1, 3, 40, 40, 4, torch.float32, dev())
+    with pytest.raises(RuntimeError, match="channels-last"):
+        _build_into(pyr, c1, c2)
+    a = sb.CorrBlock1D(c1, c2)
+    b = sb.CorrBlock1D(f1, f2)
+    assert torch.equal(a.corr_pyramid[0], b.corr_pyramid[0])
+
+
+def test_build_channels_last_backward(sb):
+    """Training with channels-last feature maps: gradients equal those of the NCHW path."""
+    from gpu_util import dev
+    g = torch.Generator(device="cpu").manual_seed(6)
+    f1 = torch.randn(1, 64, 4, 96, generator=g).to(dev())
+    f2 = torch.randn(1, 64, 4, 96, generator=g).to(dev())
+    coords = (torch.arange(96, dtype=torch.float32).view(1, 1, 1, 96).expand(1, 2, 4, 96)
+              - torch.rand(1, 2, 4, 96, generator=g) * 20).to(dev())
+    grads = []
+    for cl in (False, True):
+        a = f1.clone().requires_grad_(True)
+        b = f2.clone().requires_grad_(True)
+        x, y = (a, b)
+        if cl:
+            x = a.contiguous(memory_format=torch.channels_last)
+            y = b.contiguous(memory_format=torch.channels_last)
+        blk = sb.CorrBlock1D(x, y)
+        (blk(coords).square().sum() + blk(coords + 0.3).sum()).backward()
+        grads.append((a.grad.clone(), b.grad.clone()))
+    for k in range(2):
+        assert rel_max(grads[1][k].cpu().numpy(), grads[0][k].cpu().numpy()) < 1e-5
