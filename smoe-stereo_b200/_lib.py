@@ -27,7 +27,7 @@ SYMBOLS = (
     "smoe_corr_pyramid_layout", "smoe_corr_build_workspace_bytes", "smoe_corr_build",
     "smoe_corr_lookup", "smoe_corr_lookup_bwd", "smoe_corr_fold_pyramid_grad",
     "smoe_corr_debug_set_timeline", "smoe_corr_build_bwd", "smoe_corr_lookup_update",
-    "smoe_corr_lookup_bwd_batched", "smoe_corr_lookup_conv1x1",
+    "smoe_corr_lookup_bwd_batched", "smoe_corr_lookup_conv1x1", "smoe_corr_debug_set_lookup_kernel",
 )
 
 
@@ -75,6 +75,8 @@ def _declare(L: ctypes.CDLL) -> None:
     L.smoe_corr_build_bwd.restype = i32
     L.smoe_corr_debug_set_timeline.argtypes = [vp]
     L.smoe_corr_debug_set_timeline.restype = None
+    L.smoe_corr_debug_set_lookup_kernel.argtypes = [i32]
+    L.smoe_corr_debug_set_lookup_kernel.restype = None
     for name in ("smoe_corr_pyramid_layout", "smoe_corr_build", "smoe_corr_lookup",
                  "smoe_corr_lookup_bwd", "smoe_corr_fold_pyramid_grad"):
         getattr(L, name).restype = i32

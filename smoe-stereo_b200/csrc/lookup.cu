@@ -246,6 +246,128 @@ lookup_fwd_pair_kernel(PyrDev pyr, const float* __restrict__ coords, long long c
   }
 }
 
+// ------------------------------------------------------------------- forward (thread per pixel)
+// The lane-group kernels above spend most of their issue slots on per-pixel scalar work that every
+// warp repeats for only 4 (pair kernel: 8 lanes per pixel) or 8 pixels: ncu shows the pair kernel
+// at cfg3 with 18.8 M warp-instructions per launch (314 per warp, IPC 2.8 of 4) and it takes 24 us
+// even when the volume is L2-resident -- it is issue-bound, not DRAM-bound
+// (tools/issue_bound_probe.py, profiles/r01/README.md).  Here ONE thread owns a pixel:
+//  * per level pair it issues the NCH aligned 16-byte loads of the level-2pr segment up front
+//    (NP*NCH = 12 independent loads in flight per thread for fp32, no shared memory, no shuffles),
+//  * the data-dependent window start inside the aligned segment is one of EPL positions: it is
+//    applied with log2(EPL) rounds of register selects (no dynamic register indexing),
+//  * the coarse level of the pair is recomputed as (a+b)*0.5f like lookup_fwd_pair_kernel
+//    (bit-identical to the stored level),
+//  * lane == pixel, so every output channel is stored as one coalesced 128-byte line per warp
+//    straight from registers.
+// ~7x fewer warp-instructions per pixel; the uncoalesced 16-byte loads cost L1 wavefronts
+// instead (32 per load instruction), which is not the binding resource.
+template <int N, int BITS>
+__device__ __forceinline__ void shift_down(float (&a)[N], int s) {   // a[j] <- a[j + s], 0 <= s < 2^BITS
+#pragma unroll
+  for (int bit = BITS - 1; bit >= 0; --bit) {
+    const bool on = (s >> bit) & 1;
+#pragma unroll
+    for (int j = 0; j + (1 << bit) < N; ++j) a[j] = on ? a[j + (1 << bit)] : a[j];
+  }
+}
+
+template <typename VT, typename OT, int R, int NL, bool STREAM>
+__global__ void __launch_bounds__(128)
+lookup_fwd_px_kernel(PyrDev pyr, const float* __restrict__ coords, long long coords_bstride,
+                     float coord_scale, OT* __restrict__ out, int HW, CoordUpd upd) {
+  constexpr int EPL = Vec16<VT>::N;
+  constexpr int LOG_EPL = (EPL == 4) ? 2 : 3;
+  constexpr int RD = 2 * R + 1;
+  constexpr int NP = (NL + 1) / 2;
+  constexpr int SEG = 4 * R + 4;                              // fine elements under the coarse window
+  constexpr int NCH = (EPL - 2 + SEG + EPL - 1) / EPL;        // chunks a segment can span
+  constexpr int NV = NCH * EPL;
+  static_assert(R == 4, "window offsets below assume radius 4");
+
+  pdl_wait();
+  const int b = blockIdx.y;
+  const int hw = blockIdx.x * blockDim.x + threadIdx.x;
+  if (hw >= HW) return;
+  const float x0 = fetch_coord(coords, coords_bstride, upd, b, hw, true) * coord_scale;
+  const long long row = (long long)b * HW + hw;
+
+  float v[NP][NV];
+  float dxf[NP], dxc[NP];
+  int sh[NP];                       // S - EPL*cs: where the segment starts inside its first chunk (even)
+  int odd[NP];                      // basef - S - R: 0 or 1 (-1: parked coordinate, everything is zero)
+  int csv[NP];                      // first chunk of the segment
+  float lscale = 1.0f;
+#pragma unroll
+  for (int pr = 0; pr < NP; ++pr) {
+    const int lf = 2 * pr;
+    int basef, basec;
+    split_coord(x0 * lscale, R, basef, dxf[pr]);
+    split_coord(x0 * lscale * 0.5f, R, basec, dxc[pr]);
+    lscale *= 0.25f;
+    const int S = 2 * basec;
+    const int cs = S >> LOG_EPL;
+    sh[pr] = S - (cs << LOG_EPL);
+    csv[pr] = cs;
+    const int o = basef - S - R;
+    odd[pr] = (o == 0 || o == 1) ? o : -1;
+    const int width = pyr.width[lf];
+    const int nchunks = (width + EPL - 1) >> LOG_EPL;
+    const VT* src = static_cast<const VT*>(pyr.ptr[lf]) + row * pyr.pitch[lf] + (long long)cs * EPL;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      const int ci = cs + j;
+      float t[EPL];
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) t[e] = 0.f;
+      // the last chunk is only needed when the segment does not start at the chunk boundary
+      const bool need = odd[pr] >= 0 && (j < NCH - 1 || sh[pr] + SEG > (NCH - 1) * EPL) &&
+                        (unsigned)ci < (unsigned)nchunks;
+      if (need) Vec16<VT>::template load<STREAM>(src + j * EPL, t);
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) v[pr][j * EPL + e] = t[e];
+    }
+    if (__builtin_expect((cs + NCH) * EPL > width, 0)) {       // rare: segment reaches the row tail
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+        if (cs * EPL + i >= width) v[pr][i] = 0.f;
+    }
+  }
+  pdl_launch_dependents();
+
+  OT* dst = out + (long long)b * (NL * RD) * HW + hw;
+#pragma unroll
+  for (int pr = 0; pr < NP; ++pr) {
+    const int lf = 2 * pr;
+    if (2 * pr + 1 < NL) {
+      // coarse level of the pair: pair averages; pc[j] is coarse column cs*EPL/2 + j, columns >= wc
+      // do not exist (negative ones come from chunks that were never loaded: already zero)
+      const int wc = pyr.width[lf + 1];
+      float pc[NV / 2];
+#pragma unroll
+      for (int j = 0; j < NV / 2; ++j) {
+        float a = (v[pr][2 * j] + v[pr][2 * j + 1]) * 0.5f;
+        if (sizeof(VT) == 2) a = __half2float(__float2half_rn(a));     // stored level is fp16
+        pc[j] = a;
+      }
+      if (__builtin_expect((csv[pr] + NCH) * (EPL / 2) > wc, 0)) {
+#pragma unroll
+        for (int j = 0; j < NV / 2; ++j)
+          if (csv[pr] * (EPL / 2) + j >= wc) pc[j] = 0.f;
+      }
+      shift_down<NV / 2, LOG_EPL - 1>(pc, sh[pr] >> 1);
+      OT* d1 = dst + (long long)(lf + 1) * RD * HW;
+#pragma unroll
+      for (int k = 0; k < RD; ++k) d1[(long long)k * HW] = lerp_ref<OT>(pc[k], pc[k + 1], dxc[pr]);
+    }
+    // fine level: window starts R + odd elements after the segment start
+    shift_down<NV, LOG_EPL>(v[pr], sh[pr] + (odd[pr] > 0 ? 1 : 0));
+    OT* d0 = dst + (long long)lf * RD * HW;
+#pragma unroll
+    for (int k = 0; k < RD; ++k) d0[(long long)k * HW] = lerp_ref<OT>(v[pr][R + k], v[pr][R + k + 1], dxf[pr]);
+  }
+}
+
 // ---------------------------------------------------------------------------- forward (generic)
 template <typename VT, typename OT>
 __global__ void __launch_bounds__(128)
@@ -756,13 +878,42 @@ static void launch_fwd_pair(const PyrDev& d, const float* coords, long long cbs,
                   cbs, cs, static_cast<OT*>(out), HW, upd);
 }
 
+// SMOE_CORR_LOOKUP_KERNEL=px|pair|vec forces one forward kernel (A/B experiments, parity tests)
+static const int g_fwd_kernel_env = [] {
+  const char* e = getenv("SMOE_CORR_LOOKUP_KERNEL");
+  if (!e) return 0;
+  return e[0] == 'p' && e[1] == 'x' ? 1 : (e[0] == 'p' ? 2 : (e[0] == 'v' ? 3 : 0));
+}();
+static thread_local int g_fwd_kernel_tls = -1;       // smoe_corr_debug_set_lookup_kernel
+#define g_fwd_kernel (g_fwd_kernel_tls >= 0 ? g_fwd_kernel_tls : g_fwd_kernel_env)
+
+template <typename VT, typename OT, int NL>
+static void launch_fwd_px(const PyrDev& d, const float* coords, long long cbs, float cs, void* out,
+                          int HW, int B, cudaStream_t st, const CoordUpd& upd) {
+  constexpr int TPB = 128;
+  dim3 grid((HW + TPB - 1) / TPB, B);
+  const bool big = volume_exceeds_l2(d, (long long)HW * B, (int)sizeof(VT));
+  if (big)
+    launch_kernel(lookup_fwd_px_kernel<VT, OT, 4, NL, true>, grid, dim3(TPB), 0, st, d, coords, cbs, cs,
+                  static_cast<OT*>(out), HW, upd);
+  else
+    launch_kernel(lookup_fwd_px_kernel<VT, OT, 4, NL, false>, grid, dim3(TPB), 0, st, d, coords, cbs, cs,
+                  static_cast<OT*>(out), HW, upd);
+}
+
 template <typename VT, typename OT>
 static void dispatch_fwd_vec(int NL, const PyrDev& d, const float* coords, long long cbs, float cs,
                              void* out, int HW, int B, cudaStream_t st, const CoordUpd& upd) {
+  if (g_fwd_kernel == 1 && (NL == 2 || NL == 4)) {
+    if (NL == 4) launch_fwd_px<VT, OT, 4>(d, coords, cbs, cs, out, HW, B, st, upd);
+    else launch_fwd_px<VT, OT, 2>(d, coords, cbs, cs, out, HW, B, st, upd);
+    return;
+  }
   // Volumes that stream from DRAM: two contiguous segments per pixel instead of four windows
   // (cfg3: 31.3 -> 26.8 us).  L2-resident volumes stay on the 4-lane kernel (3.65 vs 4.04 us at
   // cfg1: that regime is latency-bound and the pair kernel does more work per pixel).
-  const bool pair = volume_exceeds_l2(d, (long long)HW * B, (int)sizeof(VT)) || g_force_pair;
+  const bool pair = (volume_exceeds_l2(d, (long long)HW * B, (int)sizeof(VT)) || g_force_pair ||
+                     g_fwd_kernel == 2) && g_fwd_kernel != 3;
   if (!g_no_pair && pair && (NL == 2 || NL == 4)) {
     if (NL == 4) launch_fwd_pair<VT, OT, 2>(d, coords, cbs, cs, out, HW, B, st, upd);
     else launch_fwd_pair<VT, OT, 1>(d, coords, cbs, cs, out, HW, B, st, upd);
@@ -862,6 +1013,8 @@ static int lookup_impl(const smoe_pyramid_t* pyr, const float* coords, int64_t c
 }  // namespace smoe
 
 extern "C" {
+
+void smoe_corr_debug_set_lookup_kernel(int which) { smoe::g_fwd_kernel_tls = which; }
 
 int smoe_corr_lookup(const smoe_pyramid_t* pyr, const float* coords, int64_t coords_batch_stride,
                      float coord_scale, int radius, void* out, int out_dtype,

@@ -132,3 +132,33 @@ def test_pair_kernel_equals_window_kernel_bitwise(sb, oracle, dtype, monkeypatch
         want = oracle.c_lookup([np.ascontiguousarray(x) for x in lv],
                                np.ascontiguousarray(coords[:1, :, :20].cpu().numpy()), 4)
         assert rel_max(out_small.cpu().numpy(), want) < ORACLE_TOL
+
+
+@pytest.mark.parametrize("dtype,levels", [(torch.float32, 4), (torch.float16, 4), (torch.float32, 2)])
+def test_thread_per_pixel_kernel_equals_lane_group_kernels_bitwise(sb, dtype, levels):
+    """lookup_fwd_px_kernel (one thread per pixel, register shift network) against the four-window
+    and level-pair lane-group kernels on the same pyramid: bit for bit, including out-of-range,
+    integer and non-finite coordinates, odd widths at every level and rows shorter than a segment."""
+    from gpu_util import dev, make_coords
+    from smoe_stereo_b200 import _lib
+    L = _lib.lib()
+    for (B, C, H, W1, W2) in [(2, 32, 9, 77, 77), (1, 16, 5, 40, 312), (1, 16, 3, 33, 22), (2, 16, 4, 50, 9)]:
+        g = torch.Generator(device="cpu").manual_seed(W2)
+        f1 = torch.randn(B, C, H, W1, generator=g).to(dev()).to(dtype)
+        f2 = torch.randn(B, C, H, W2, generator=g).to(dev()).to(dtype)
+        cls = sb.CorrBlock1D if dtype == torch.float32 else sb.CorrBlockFast1D
+        blk = cls(f1, f2, num_levels=levels)
+        coords = torch.from_numpy(make_coords(B, H, W1, W2, 3, seed=W1)).to(dev())
+        coords[0, 0, 0, 0, :6] = torch.tensor([float("nan"), float("inf"), -float("inf"), 3e9, -0.0, W2 - 1.0])
+        coords[1, 0, 0, 1, :4] = torch.tensor([-4.0, -4.5, W2 + 3.999, W2 + 4.0])
+        outs = {}
+        try:
+            for which, name in ((1, "px"), (2, "pair"), (3, "vec")):
+                L.smoe_corr_debug_set_lookup_kernel(which)
+                outs[name] = [blk(coords[t]).clone() for t in range(3)]
+        finally:
+            L.smoe_corr_debug_set_lookup_kernel(-1)
+        for t in range(3):
+            assert torch.equal(outs["px"][t], outs["vec"][t]), (B, C, H, W1, W2, t)
+            assert torch.equal(outs["pair"][t], outs["vec"][t])
+            assert torch.isfinite(outs["px"][t]).all()
