@@ -272,48 +272,55 @@ __device__ __forceinline__ void shift_down(float (&a)[N], int s) {   // a[j] <- 
   }
 }
 
-template <typename VT, typename OT, int R, int NL, bool STREAM>
-__global__ void __launch_bounds__(128)
+// SPLIT: blockDim.y = number of level pairs and each thread handles ONE pair of its pixel (half
+// the dependent instruction chain and registers per thread, twice the threads): for L2-resident
+// volumes, where the kernel is bound by the latency of that chain rather than by throughput.
+template <typename VT, typename OT, int R, int NL, bool STREAM, bool SPLIT>
+__global__ void __launch_bounds__(256)
 lookup_fwd_px_kernel(PyrDev pyr, const float* __restrict__ coords, long long coords_bstride,
                      float coord_scale, OT* __restrict__ out, int HW, CoordUpd upd) {
   constexpr int EPL = Vec16<VT>::N;
   constexpr int LOG_EPL = (EPL == 4) ? 2 : 3;
   constexpr int RD = 2 * R + 1;
   constexpr int NP = (NL + 1) / 2;
+  constexpr int NPT = SPLIT ? 1 : NP;                         // pairs per thread
   constexpr int SEG = 4 * R + 4;                              // fine elements under the coarse window
   constexpr int NCH = (EPL - 2 + SEG + EPL - 1) / EPL;        // chunks a segment can span
   constexpr int NV = NCH * EPL;
-  static_assert(R == 4, "window offsets below assume radius 4");
+  static_assert(R == 4 && NP <= 2, "window offsets / level scales below assume radius 4, <= 4 levels");
 
   pdl_wait();
   const int b = blockIdx.y;
   const int hw = blockIdx.x * blockDim.x + threadIdx.x;
+  const int pr0 = SPLIT ? (int)threadIdx.y : 0;
   if (hw >= HW) return;
-  const float x0 = fetch_coord(coords, coords_bstride, upd, b, hw, true) * coord_scale;
+  const float x0 = fetch_coord(coords, coords_bstride, upd, b, hw, pr0 == 0) * coord_scale;
   const long long row = (long long)b * HW + hw;
 
-  float v[NP][NV];
-  float dxf[NP], dxc[NP];
-  int sh[NP];                       // S - EPL*cs: where the segment starts inside its first chunk (even)
-  int odd[NP];                      // basef - S - R: 0 or 1 (-1: parked coordinate, everything is zero)
-  int csv[NP];                      // first chunk of the segment
-  float lscale = 1.0f;
+  float v[NPT][NV];
+  float dxf[NPT], dxc[NPT];
+  int sh[NPT];                      // S - EPL*cs: where the segment starts inside its first chunk (even)
+  int odd[NPT];                     // basef - S - R: 0 or 1 (-1: parked coordinate, everything is zero)
+  int csv[NPT];                     // first chunk of the segment
 #pragma unroll
-  for (int pr = 0; pr < NP; ++pr) {
+  for (int i = 0; i < NPT; ++i) {
+    const int pr = pr0 + i;
     const int lf = 2 * pr;
+    const float lscale = pr == 0 ? 1.0f : 0.25f;
     int basef, basec;
-    split_coord(x0 * lscale, R, basef, dxf[pr]);
-    split_coord(x0 * lscale * 0.5f, R, basec, dxc[pr]);
-    lscale *= 0.25f;
+    split_coord(x0 * lscale, R, basef, dxf[i]);
+    split_coord(x0 * lscale * 0.5f, R, basec, dxc[i]);
     const int S = 2 * basec;
     const int cs = S >> LOG_EPL;
-    sh[pr] = S - (cs << LOG_EPL);
-    csv[pr] = cs;
+    sh[i] = S - (cs << LOG_EPL);
+    csv[i] = cs;
     const int o = basef - S - R;
-    odd[pr] = (o == 0 || o == 1) ? o : -1;
-    const int width = pyr.width[lf];
+    odd[i] = (o == 0 || o == 1) ? o : -1;
+    // (selects instead of pyr.x[lf]: a runtime index would copy the parameter struct to local memory)
+    const int width = (pr == 0 || NP == 1) ? pyr.width[0] : pyr.width[2];
     const int nchunks = (width + EPL - 1) >> LOG_EPL;
-    const VT* src = static_cast<const VT*>(pyr.ptr[lf]) + row * pyr.pitch[lf] + (long long)cs * EPL;
+    const VT* src = static_cast<const VT*>((pr == 0 || NP == 1) ? pyr.ptr[0] : pyr.ptr[2]) +
+                    row * ((pr == 0 || NP == 1) ? pyr.pitch[0] : pyr.pitch[2]) + (long long)cs * EPL;
 #pragma unroll
     for (int j = 0; j < NCH; ++j) {
       const int ci = cs + j;
@@ -321,50 +328,51 @@ lookup_fwd_px_kernel(PyrDev pyr, const float* __restrict__ coords, long long coo
 #pragma unroll
       for (int e = 0; e < EPL; ++e) t[e] = 0.f;
       // the last chunk is only needed when the segment does not start at the chunk boundary
-      const bool need = odd[pr] >= 0 && (j < NCH - 1 || sh[pr] + SEG > (NCH - 1) * EPL) &&
+      const bool need = odd[i] >= 0 && (j < NCH - 1 || sh[i] + SEG > (NCH - 1) * EPL) &&
                         (unsigned)ci < (unsigned)nchunks;
       if (need) Vec16<VT>::template load<STREAM>(src + j * EPL, t);
 #pragma unroll
-      for (int e = 0; e < EPL; ++e) v[pr][j * EPL + e] = t[e];
+      for (int e = 0; e < EPL; ++e) v[i][j * EPL + e] = t[e];
     }
     if (__builtin_expect((cs + NCH) * EPL > width, 0)) {       // rare: segment reaches the row tail
 #pragma unroll
-      for (int i = 0; i < NV; ++i)
-        if (cs * EPL + i >= width) v[pr][i] = 0.f;
+      for (int k = 0; k < NV; ++k)
+        if (cs * EPL + k >= width) v[i][k] = 0.f;
     }
   }
   pdl_launch_dependents();
 
   OT* dst = out + (long long)b * (NL * RD) * HW + hw;
 #pragma unroll
-  for (int pr = 0; pr < NP; ++pr) {
+  for (int i = 0; i < NPT; ++i) {
+    const int pr = pr0 + i;
     const int lf = 2 * pr;
     if (2 * pr + 1 < NL) {
       // coarse level of the pair: pair averages; pc[j] is coarse column cs*EPL/2 + j, columns >= wc
       // do not exist (negative ones come from chunks that were never loaded: already zero)
-      const int wc = pyr.width[lf + 1];
+      const int wc = (pr == 0 || NL < 4) ? pyr.width[1] : pyr.width[3];
       float pc[NV / 2];
 #pragma unroll
       for (int j = 0; j < NV / 2; ++j) {
-        float a = (v[pr][2 * j] + v[pr][2 * j + 1]) * 0.5f;
+        float a = (v[i][2 * j] + v[i][2 * j + 1]) * 0.5f;
         if (sizeof(VT) == 2) a = __half2float(__float2half_rn(a));     // stored level is fp16
         pc[j] = a;
       }
-      if (__builtin_expect((csv[pr] + NCH) * (EPL / 2) > wc, 0)) {
+      if (__builtin_expect((csv[i] + NCH) * (EPL / 2) > wc, 0)) {
 #pragma unroll
         for (int j = 0; j < NV / 2; ++j)
-          if (csv[pr] * (EPL / 2) + j >= wc) pc[j] = 0.f;
+          if (csv[i] * (EPL / 2) + j >= wc) pc[j] = 0.f;
       }
-      shift_down<NV / 2, LOG_EPL - 1>(pc, sh[pr] >> 1);
+      shift_down<NV / 2, LOG_EPL - 1>(pc, sh[i] >> 1);
       OT* d1 = dst + (long long)(lf + 1) * RD * HW;
 #pragma unroll
-      for (int k = 0; k < RD; ++k) d1[(long long)k * HW] = lerp_ref<OT>(pc[k], pc[k + 1], dxc[pr]);
+      for (int k = 0; k < RD; ++k) d1[(long long)k * HW] = lerp_ref<OT>(pc[k], pc[k + 1], dxc[i]);
     }
     // fine level: window starts R + odd elements after the segment start
-    shift_down<NV, LOG_EPL>(v[pr], sh[pr] + (odd[pr] > 0 ? 1 : 0));
+    shift_down<NV, LOG_EPL>(v[i], sh[i] + (odd[i] > 0 ? 1 : 0));
     OT* d0 = dst + (long long)lf * RD * HW;
 #pragma unroll
-    for (int k = 0; k < RD; ++k) d0[(long long)k * HW] = lerp_ref<OT>(v[pr][R + k], v[pr][R + k + 1], dxf[pr]);
+    for (int k = 0; k < RD; ++k) d0[(long long)k * HW] = lerp_ref<OT>(v[i][R + k], v[i][R + k + 1], dxf[i]);
   }
 }
 
@@ -887,26 +895,47 @@ static const int g_fwd_kernel_env = [] {
 static thread_local int g_fwd_kernel_tls = -1;       // smoe_corr_debug_set_lookup_kernel
 #define g_fwd_kernel (g_fwd_kernel_tls >= 0 ? g_fwd_kernel_tls : g_fwd_kernel_env)
 
+// experiment switches for the thread-per-pixel kernel: pixels per CTA, one thread per level pair
+static const int g_px_tpb = [] { const char* e = getenv("SMOE_CORR_PX_TPB"); return e ? atoi(e) : 0; }();
+static const int g_px_split = [] { const char* e = getenv("SMOE_CORR_PX_SPLIT"); return e ? atoi(e) : -1; }();
+
 template <typename VT, typename OT, int NL>
 static void launch_fwd_px(const PyrDev& d, const float* coords, long long cbs, float cs, void* out,
                           int HW, int B, cudaStream_t st, const CoordUpd& upd) {
-  constexpr int TPB = 128;
-  dim3 grid((HW + TPB - 1) / TPB, B);
+  constexpr int NP = (NL + 1) / 2;
   const bool big = volume_exceeds_l2(d, (long long)HW * B, (int)sizeof(VT));
-  if (big)
-    launch_kernel(lookup_fwd_px_kernel<VT, OT, 4, NL, true>, grid, dim3(TPB), 0, st, d, coords, cbs, cs,
-                  static_cast<OT*>(out), HW, upd);
-  else
-    launch_kernel(lookup_fwd_px_kernel<VT, OT, 4, NL, false>, grid, dim3(TPB), 0, st, d, coords, cbs, cs,
-                  static_cast<OT*>(out), HW, upd);
+  // measured (tools/px_sweep.sh): 32 pixels per CTA everywhere; one thread per level pair for
+  // volumes beyond L2 (cfg2 10.2 -> 8.9 us, cfg3 fp16 18.6 -> 12.4 us) and for fp16 volumes
+  // (cfg1 3.40 -> 3.16 us), one thread per pixel for L2-resident fp32 volumes (cfg1 3.02 vs 3.08 us)
+  const bool split = NP > 1 && (g_px_split >= 0 ? g_px_split != 0 : (big || sizeof(VT) == 2));
+  int tpb = (g_px_tpb == 32 || g_px_tpb == 64 || g_px_tpb == 128) ? g_px_tpb : 32;
+  dim3 grid((HW + tpb - 1) / tpb, B);
+  OT* o = static_cast<OT*>(out);
+  if (split) {
+    constexpr int NLS = NP > 1 ? NL : 4;      // (never launched for NP == 1; avoids instantiating it)
+    dim3 block(tpb, NP);
+    if (big) launch_kernel(lookup_fwd_px_kernel<VT, OT, 4, NLS, true, true>, grid, block, 0, st, d, coords, cbs, cs, o, HW, upd);
+    else launch_kernel(lookup_fwd_px_kernel<VT, OT, 4, NLS, false, true>, grid, block, 0, st, d, coords, cbs, cs, o, HW, upd);
+  } else {
+    dim3 block(tpb);
+    if (big) launch_kernel(lookup_fwd_px_kernel<VT, OT, 4, NL, true, false>, grid, block, 0, st, d, coords, cbs, cs, o, HW, upd);
+    else launch_kernel(lookup_fwd_px_kernel<VT, OT, 4, NL, false, false>, grid, block, 0, st, d, coords, cbs, cs, o, HW, upd);
+  }
 }
 
 template <typename VT, typename OT>
 static void dispatch_fwd_vec(int NL, const PyrDev& d, const float* coords, long long cbs, float cs,
                              void* out, int HW, int B, cudaStream_t st, const CoordUpd& upd) {
-  if (g_fwd_kernel == 1 && (NL == 2 || NL == 4)) {
-    if (NL == 4) launch_fwd_px<VT, OT, 4>(d, coords, cbs, cs, out, HW, B, st, upd);
-    else launch_fwd_px<VT, OT, 2>(d, coords, cbs, cs, out, HW, B, st, upd);
+  // Default: the thread-per-pixel kernel (faster than both lane-group kernels at every size and
+  // dtype measured, tools/lookup_kernels_probe.py).  The lane-group kernels stay selectable
+  // (smoe_corr_debug_set_lookup_kernel / SMOE_CORR_LOOKUP_KERNEL) as bit-exact cross-checks.
+  if (g_fwd_kernel == 0 || g_fwd_kernel == 1) {
+    switch (NL) {
+      case 1: launch_fwd_px<VT, OT, 1>(d, coords, cbs, cs, out, HW, B, st, upd); break;
+      case 2: launch_fwd_px<VT, OT, 2>(d, coords, cbs, cs, out, HW, B, st, upd); break;
+      case 3: launch_fwd_px<VT, OT, 3>(d, coords, cbs, cs, out, HW, B, st, upd); break;
+      default: launch_fwd_px<VT, OT, 4>(d, coords, cbs, cs, out, HW, B, st, upd); break;
+    }
     return;
   }
   // Volumes that stream from DRAM: two contiguous segments per pixel instead of four windows
