@@ -16,12 +16,15 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-bool pdl_enabled() {
-  static const bool on = [] {
-    const char* e = getenv("SMOE_CORR_PDL");     // opt-in: measured slower on B200 for this path
-    return e && e[0] && e[0] != '0';
+// SMOE_CORR_PDL: unset -> 2 (programmatic dependent launch only for the kernels that measured
+// faster with it: the thread-per-pixel lookup), 0 -> never, anything else -> every kernel.
+int pdl_mode() {
+  static const int mode = [] {
+    const char* e = getenv("SMOE_CORR_PDL");
+    if (!e || !e[0]) return 2;
+    return e[0] == '0' ? 0 : 1;
   }();
-  return on;
+  return mode;
 }
 
 int validate_pyramid(const smoe_pyramid_t* p, const char* who) {

@@ -42,14 +42,15 @@ inline int check_launch(const char* what) {
 
 // Programmatic dependent launch (PDL): the kernel may become resident while its predecessor in
 // the stream is still draining; it must execute pdl_wait() before touching global memory.
-// Opt-in with SMOE_CORR_PDL=1: on B200 back-to-back lookups measured ~10% SLOWER with PDL
-// (profiles/r01/README.md), so plain stream-ordered launches are the default.
-bool pdl_enabled();   // api.cu
+// On B200 back-to-back lane-group lookups measured ~10% SLOWER with PDL, the thread-per-pixel
+// lookup ~6% faster (2.82 vs 3.01 us at cfg1; profiles/r01/README.md), so by default only launches
+// that ask for it (prefer_pdl) get the attribute.  SMOE_CORR_PDL=0 / 1 forces it off / on everywhere.
+int pdl_mode();   // api.cu: 0 never, 1 always, 2 where preferred
 
 // cluster_x > 1 launches thread-block clusters of that many CTAs along x (grid.x a multiple of it)
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_kernel_cluster(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
-                                         cudaStream_t st, unsigned cluster_x, Args... args) {
+inline cudaError_t launch_kernel_ex(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                    cudaStream_t st, unsigned cluster_x, bool prefer_pdl, Args... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -57,7 +58,8 @@ inline cudaError_t launch_kernel_cluster(void (*kern)(KArgs...), dim3 grid, dim3
   cfg.stream = st;
   cudaLaunchAttribute at[2];
   unsigned n = 0;
-  if (pdl_enabled()) {
+  const int mode = pdl_mode();
+  if (mode == 1 || (mode == 2 && prefer_pdl)) {
     at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[n].val.programmaticStreamSerializationAllowed = 1;
     ++n;
@@ -74,9 +76,19 @@ inline cudaError_t launch_kernel_cluster(void (*kern)(KArgs...), dim3 grid, dim3
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel_cluster(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                         cudaStream_t st, unsigned cluster_x, Args... args) {
+  return launch_kernel_ex(kern, grid, block, smem, st, cluster_x, false, args...);
+}
+template <typename... KArgs, typename... Args>
 inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
                                  cudaStream_t st, Args... args) {
-  return launch_kernel_cluster(kern, grid, block, smem, st, 1u, args...);
+  return launch_kernel_ex(kern, grid, block, smem, st, 1u, false, args...);
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                     cudaStream_t st, Args... args) {
+  return launch_kernel_ex(kern, grid, block, smem, st, 1u, true, args...);
 }
 
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

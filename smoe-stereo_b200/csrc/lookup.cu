@@ -914,12 +914,12 @@ static void launch_fwd_px(const PyrDev& d, const float* coords, long long cbs, f
   if (split) {
     constexpr int NLS = NP > 1 ? NL : 4;      // (never launched for NP == 1; avoids instantiating it)
     dim3 block(tpb, NP);
-    if (big) launch_kernel(lookup_fwd_px_kernel<VT, OT, 4, NLS, true, true>, grid, block, 0, st, d, coords, cbs, cs, o, HW, upd);
-    else launch_kernel(lookup_fwd_px_kernel<VT, OT, 4, NLS, false, true>, grid, block, 0, st, d, coords, cbs, cs, o, HW, upd);
+    if (big) launch_kernel_pdl(lookup_fwd_px_kernel<VT, OT, 4, NLS, true, true>, grid, block, 0, st, d, coords, cbs, cs, o, HW, upd);
+    else launch_kernel_pdl(lookup_fwd_px_kernel<VT, OT, 4, NLS, false, true>, grid, block, 0, st, d, coords, cbs, cs, o, HW, upd);
   } else {
     dim3 block(tpb);
-    if (big) launch_kernel(lookup_fwd_px_kernel<VT, OT, 4, NL, true, false>, grid, block, 0, st, d, coords, cbs, cs, o, HW, upd);
-    else launch_kernel(lookup_fwd_px_kernel<VT, OT, 4, NL, false, false>, grid, block, 0, st, d, coords, cbs, cs, o, HW, upd);
+    if (big) launch_kernel_pdl(lookup_fwd_px_kernel<VT, OT, 4, NL, true, false>, grid, block, 0, st, d, coords, cbs, cs, o, HW, upd);
+    else launch_kernel_pdl(lookup_fwd_px_kernel<VT, OT, 4, NL, false, false>, grid, block, 0, st, d, coords, cbs, cs, o, HW, upd);
   }
 }
 
