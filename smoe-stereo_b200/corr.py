@@ -195,12 +195,14 @@ def _build_backward(gp: FusedPyramid, fmap1: torch.Tensor, fmap2: torch.Tensor):
     return df1.to(fmap1.dtype), df2.to(fmap2.dtype)
 
 
-def _batched_smem_bytes(W2: int, num_levels: int, grad_elem: int) -> int:
+def _batched_smem_bytes(W2: int, num_levels: int) -> int:
+    """Upper bound of the shared memory smoe_corr_lookup_bwd_batched needs per CTA: the gradient
+    rows of a 32-pixel tile (all levels, each padded to 4 words, row padded to a bank offset)."""
     off, w = 0, W2
     for _ in range(num_levels):
         off += (w + 3) // 4 * 4
         w //= 2
-    return 32 * (off + 32) * 4 + 4 * (num_levels * 9 * (32 + 32 // grad_elem) * grad_elem + 32 * 4)
+    return 32 * (off + 32) * 4
 
 
 def _batchable(pyr: FusedPyramid, coords: torch.Tensor, grad_out: torch.Tensor, radius: int):
@@ -208,13 +210,10 @@ def _batchable(pyr: FusedPyramid, coords: torch.Tensor, grad_out: torch.Tensor, 
     (smoe_corr_lookup_bwd_batched), else None -> per-call accumulate path."""
     if radius != 4 or grad_out.dtype not in _DTYPE_CODE:
         return None
-    es = grad_out.element_size()
-    if (pyr.H * pyr.W1 * es) % 16 != 0 or _batched_smem_bytes(pyr.W2, pyr.num_levels, es) > 227 * 1024:
+    if _batched_smem_bytes(pyr.W2, pyr.num_levels) > 227 * 1024:
         return None
     grad_out = grad_out.contiguous()
     coords, bstride = _coords_plane(coords, pyr.B, pyr.H, pyr.W1)
-    if coords.data_ptr() % 16 or grad_out.data_ptr() % 16 or bstride % 4:
-        return None
     return coords, bstride, grad_out
 
 

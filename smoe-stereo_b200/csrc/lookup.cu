@@ -748,6 +748,111 @@ lookup_bwd_batched_kernel(const __grid_constant__ BwdBatch batch, const BatchedG
   }
 }
 
+// Second version of the batched backward: warp = pyramid level, lane = pixel of the 32-pixel tile.
+// The gradient rows of a pixel are private to it and the levels occupy disjoint parts of the row,
+// so the T iterations need NO barrier and no shared-memory staging of the gradient tiles: each warp
+// streams its 9 gradient channels (+ the coordinate) of iteration t straight from global memory
+// into registers -- lane = pixel makes every load one coalesced line -- two iterations ahead of
+// the one it is scattering.  One coordinate split per (pixel, level, iteration) instead of two,
+// no cp.async address arithmetic, no per-iteration __syncthreads: ~2.2x fewer warp-instructions
+// than lookup_bwd_batched_kernel, and no 16-byte alignment requirement on the gradient planes.
+// Same accumulation order per element (iterations ascending) => bit-identical results.
+template <typename GT, int NL>
+__global__ void __launch_bounds__(128)
+lookup_bwd_lvl_kernel(const __grid_constant__ BwdBatch batch, const BatchedGeom geo,
+                      float* __restrict__ g0_out, long long g0_pitch, int HW, int accumulate) {
+#ifndef SMOE_BWD_LVL_DEPTH
+#define SMOE_BWD_LVL_DEPTH 5
+#endif
+  constexpr int R = 4, RD = 9, NC = NL * RD, kDepth = SMOE_BWD_LVL_DEPTH;   // register ring: kDepth-1 iterations in flight
+  extern __shared__ __align__(16) uint8_t s_raw[];
+  float* s_rows = reinterpret_cast<float*>(s_raw);                    // [kTilePx][rowlen]
+
+  pdl_launch_dependents();
+  pdl_wait();
+  const int tid = threadIdx.x;
+  const int l = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.y;
+  const int hw0 = blockIdx.x * kTilePx;
+  const int npx = min(kTilePx, HW - hw0);
+
+  for (int i = tid; i < kTilePx * geo.rowlen / 4; i += 128)
+    reinterpret_cast<float4*>(s_rows)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (accumulate) {
+    __syncthreads();
+    for (int pp = 0; pp < npx; ++pp)
+      for (int j = tid; j < geo.width[0]; j += 128)
+        s_rows[pp * geo.rowlen + j] = g0_out[((long long)b * HW + hw0 + pp) * g0_pitch + j];
+  }
+  __syncthreads();
+
+  if (l < NL && lane < npx) {
+    float* rowl = s_rows + lane * geo.rowlen + geo.off[l];
+    const unsigned width = (unsigned)geo.width[l];
+    const float lscale = 1.0f / (float)(1 << l);
+    const long long gofs = ((long long)b * NC + l * RD) * HW + hw0 + lane;
+    float g[kDepth][RD], x[kDepth];
+    auto load = [&](int t, float (&gt)[RD], float& xt) {
+      const GT* gp = static_cast<const GT*>(batch.gout[t]) + gofs;
+#pragma unroll
+      for (int k = 0; k < RD; ++k) gt[k] = to_float(__ldg(gp + (long long)k * HW));
+      xt = __ldg(batch.coords[t] + (long long)b * batch.coords_bstride[t] + hw0 + lane);
+    };
+    auto scatter = [&](const float (&gt)[RD], float xt) {
+      int base;
+      float dx;
+      split_coord(xt * lscale, R, base, dx);
+      // (a shared-memory atomicAdd per tap compiles to an ATOMS.CAST.SPIN loop on sm_100a: no gain)
+      float cur[RD + 1];
+      bool ok[RD + 1];
+#pragma unroll
+      for (int k = 0; k <= RD; ++k) {                 // all shared-memory loads first
+        ok[k] = (unsigned)(base + k) < width;
+        cur[k] = ok[k] ? rowl[base + k] : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k <= RD; ++k)
+        cur[k] += BwdTap<float>::eval(k > 0 ? gt[k - 1] : 0.f, k < RD ? gt[k] : 0.f, k > 0, k < RD, dx);
+#pragma unroll
+      for (int k = 0; k <= RD; ++k)
+        if (ok[k]) rowl[base + k] = cur[k];
+    };
+    const int T = batch.T;
+#pragma unroll
+    for (int u = 0; u < kDepth - 1; ++u)
+      if (u < T) load(u, g[u], x[u]);
+    for (int t0 = 0; t0 < T; t0 += kDepth) {
+#pragma unroll
+      for (int u = 0; u < kDepth; ++u) {
+        const int t = t0 + u;
+        if (t < T) {
+          if (t + kDepth - 1 < T) load(t + kDepth - 1, g[(u + kDepth - 1) % kDepth], x[(u + kDepth - 1) % kDepth]);
+          scatter(g[u], x[u]);
+        }
+      }
+    }
+  }
+  __syncthreads();                         // all scatters done before the fold reads the rows
+  const int w0 = geo.width[0];
+  for (int j = tid; j < w0; j += 128) {
+    int top = 0;
+    for (int lv = 1; lv < NL; ++lv) {
+      if ((j >> lv) >= geo.width[lv]) break;
+      top = lv;
+    }
+    const int i1 = geo.off[1] + (j >> 1), i2 = geo.off[2] + (j >> 2), i3 = geo.off[3] + (j >> 3);
+    float* out = g0_out + ((long long)b * HW + hw0) * g0_pitch + j;
+    for (int pp = 0; pp < npx; ++pp) {
+      const float* rowp = s_rows + pp * geo.rowlen;
+      float tsum = 0.f;
+      if (top >= 3) tsum = rowp[i3];
+      if (top >= 2) tsum = rowp[i2] + 0.5f * tsum;
+      if (top >= 1) tsum = rowp[i1] + 0.5f * tsum;
+      out[(long long)pp * g0_pitch] = rowp[j] + 0.5f * tsum;
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------------- fold
 // G0[j] += 0.5*(G1[j/2] + 0.5*(G2[j/4] + 0.5*G3[j/8])), stopping at the first level whose index
 // falls outside its width (the column an odd level dropped, core/corr.py:124).
@@ -1147,14 +1252,17 @@ int smoe_corr_lookup_bwd_batched(const smoe_pyramid_t* g0, int num_levels, int n
   SMOE_REQUIRE(coords && coords_batch_stride && grad_out, SMOE_ERR_INVALID_ARG, "lookup_bwd_batched: NULL array");
   SMOE_REQUIRE(g0->B <= 65535, SMOE_ERR_UNSUPPORTED, "lookup_bwd_batched: batch %d > 65535", g0->B);
   const int ges = dtype_size(grad_out_dtype);
-  SMOE_REQUIRE((HW * ges) % 16 == 0, SMOE_ERR_UNSUPPORTED,
+  // SMOE_CORR_BWD_BATCHED=staged selects the first version (cp.async-staged tiles, 16-byte rules)
+  static const bool staged = [] { const char* e = getenv("SMOE_CORR_BWD_BATCHED"); return e && e[0] == 's'; }();
+  SMOE_REQUIRE(!staged || (HW * ges) % 16 == 0, SMOE_ERR_UNSUPPORTED,
                "lookup_bwd_batched: H*W1=%lld planes are not 16-byte multiples (cp.async staging)", HW);
   BwdBatch batch;
   batch.T = num_iters;
   for (int t = 0; t < num_iters; ++t) {
     SMOE_REQUIRE(coords[t] && grad_out[t], SMOE_ERR_INVALID_ARG, "lookup_bwd_batched: NULL pointer at iteration %d", t);
-    SMOE_REQUIRE(aligned16(coords[t]) && aligned16(grad_out[t]) && coords_batch_stride[t] % 4 == 0 &&
-                     coords_batch_stride[t] >= HW,
+    SMOE_REQUIRE(coords_batch_stride[t] >= HW, SMOE_ERR_INVALID_ARG,
+                 "lookup_bwd_batched: iteration %d coords batch stride < H*W1", t);
+    SMOE_REQUIRE(!staged || (aligned16(coords[t]) && aligned16(grad_out[t]) && coords_batch_stride[t] % 4 == 0),
                  SMOE_ERR_UNSUPPORTED, "lookup_bwd_batched: iteration %d operands are not 16-byte aligned", t);
     batch.coords[t] = coords[t];
     batch.gout[t] = grad_out[t];
@@ -1173,8 +1281,12 @@ int smoe_corr_lookup_bwd_batched(const smoe_pyramid_t* g0, int num_levels, int n
   // then cover all 32 banks.  (rowlen % 32 == 0, which W2=184 happened to give with a fixed pad,
   // made every scatter an 8-way bank conflict: 810 us instead of ~200 us at config 2.)
   geo.rowlen = off + ((4 - off % 32) + 32) % 32;
+  // warp-per-level kernel: lane = pixel, so consecutive lanes hit rows `rowlen` apart at columns
+  // that advance by 2^-level per pixel; rowlen % 32 == 2 makes level 0 conflict-free (3 banks per
+  // pixel) and keeps the coarser levels at <= 2-way
+  if (!staged) geo.rowlen = off + ((2 - off % 32) + 32) % 32;
   const size_t smem = (size_t)kTilePx * geo.rowlen * 4 +
-                      kBatchedStages * ((size_t)num_levels * 9 * (kTilePx + 32 / ges) * ges + kTilePx * 4);
+                      (staged ? kBatchedStages * ((size_t)num_levels * 9 * (kTilePx + 32 / ges) * ges + kTilePx * 4) : 0);
   // (the Python side bounds this with off + 32 words per row)
   SMOE_REQUIRE(smem <= 227 * 1024, SMOE_ERR_UNSUPPORTED,
                "lookup_bwd_batched: W2=%d needs %zu bytes of shared memory per CTA", g0->width[0], smem);
@@ -1183,10 +1295,17 @@ int smoe_corr_lookup_bwd_batched(const smoe_pyramid_t* g0, int num_levels, int n
   float* out = static_cast<float*>(g0->level_ptr[0]);
 #define SMOE_LAUNCH_BATCHED(GT, NLV)                                                                     \
   do {                                                                                                   \
-    SMOE_CUDA_OK(cudaFuncSetAttribute(lookup_bwd_batched_kernel<GT, NLV>,                                \
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
-    SMOE_CUDA_OK(launch_kernel(lookup_bwd_batched_kernel<GT, NLV>, grid, dim3(kBatchedThreads), smem, st, \
-                               batch, geo, out, (long long)g0->pitch[0], (int)HW, accumulate));           \
+    if (staged) {                                                                                        \
+      SMOE_CUDA_OK(cudaFuncSetAttribute(lookup_bwd_batched_kernel<GT, NLV>,                              \
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+      SMOE_CUDA_OK(launch_kernel(lookup_bwd_batched_kernel<GT, NLV>, grid, dim3(kBatchedThreads), smem,  \
+                                 st, batch, geo, out, (long long)g0->pitch[0], (int)HW, accumulate));     \
+    } else {                                                                                             \
+      SMOE_CUDA_OK(cudaFuncSetAttribute(lookup_bwd_lvl_kernel<GT, NLV>,                                  \
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+      SMOE_CUDA_OK(launch_kernel(lookup_bwd_lvl_kernel<GT, NLV>, grid, dim3(128), smem, st, batch, geo,  \
+                                 out, (long long)g0->pitch[0], (int)HW, accumulate));                     \
+    }                                                                                                    \
   } while (0)
   const bool f16g = grad_out_dtype == SMOE_DTYPE_F16;
   switch (num_levels) {

@@ -152,7 +152,9 @@ def test_native_build_backward_vs_oracle(sb, oracle, shape):
 
 
 @pytest.mark.parametrize("shape,T,gdtype", [((2, 80, 184), 5, torch.float32), ((1, 135, 240), 3, torch.float32),
-                                            ((1, 6, 52), 50, torch.float32), ((2, 8, 40), 4, torch.float16)])
+                                            ((1, 6, 52), 50, torch.float32), ((2, 8, 40), 4, torch.float16),
+                                            ((2, 5, 37), 3, torch.float32),     # H*W1 % 4 != 0, odd widths
+                                            ((1, 3, 21), 2, torch.float16)])    # ragged 32-pixel tiles, fp16 grads
 def test_batched_backward_equals_accumulate_then_fold(sb, shape, T, gdtype):
     """smoe_corr_lookup_bwd_batched (all iterations of a step in one pass, folded in shared memory)
     == T x smoe_corr_lookup_bwd(ACCUMULATE) + smoe_corr_fold_pyramid_grad, bit for bit."""
