@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SOURCES = ["api.cu", "lookup.cu", "lookup_conv.cu", "build.cu", "build_bwd.cu"]
-HEADERS = ["common.cuh", "ptx.cuh", os.path.join("..", "..", "include", "smoe_corr.h")]
+HEADERS = ["common.cuh", "ptx.cuh", "px_gather.cuh", os.path.join("..", "..", "include", "smoe_corr.h")]
 LIB = os.path.join(HERE, "libsmoecorr.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [

@@ -16,6 +16,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "px_gather.cuh"
 
 namespace smoe {
 
@@ -262,16 +263,6 @@ lookup_fwd_pair_kernel(PyrDev pyr, const float* __restrict__ coords, long long c
 //    straight from registers.
 // ~7x fewer warp-instructions per pixel; the uncoalesced 16-byte loads cost L1 wavefronts
 // instead (32 per load instruction), which is not the binding resource.
-template <int N, int BITS>
-__device__ __forceinline__ void shift_down(float (&a)[N], int s) {   // a[j] <- a[j + s], 0 <= s < 2^BITS
-#pragma unroll
-  for (int bit = BITS - 1; bit >= 0; --bit) {
-    const bool on = (s >> bit) & 1;
-#pragma unroll
-    for (int j = 0; j + (1 << bit) < N; ++j) a[j] = on ? a[j + (1 << bit)] : a[j];
-  }
-}
-
 // SPLIT: blockDim.y = number of level pairs and each thread handles ONE pair of its pixel (half
 // the dependent instruction chain and registers per thread, twice the threads): for L2-resident
 // volumes, where the kernel is bound by the latency of that chain rather than by throughput.
@@ -279,15 +270,11 @@ template <typename VT, typename OT, int R, int NL, bool STREAM, bool SPLIT>
 __global__ void __launch_bounds__(256)
 lookup_fwd_px_kernel(PyrDev pyr, const float* __restrict__ coords, long long coords_bstride,
                      float coord_scale, OT* __restrict__ out, int HW, CoordUpd upd) {
-  constexpr int EPL = Vec16<VT>::N;
-  constexpr int LOG_EPL = (EPL == 4) ? 2 : 3;
+  using Pair = PxPair<VT, STREAM>;
   constexpr int RD = 2 * R + 1;
   constexpr int NP = (NL + 1) / 2;
   constexpr int NPT = SPLIT ? 1 : NP;                         // pairs per thread
-  constexpr int SEG = 4 * R + 4;                              // fine elements under the coarse window
-  constexpr int NCH = (EPL - 2 + SEG + EPL - 1) / EPL;        // chunks a segment can span
-  constexpr int NV = NCH * EPL;
-  static_assert(R == 4 && NP <= 2, "window offsets / level scales below assume radius 4, <= 4 levels");
+  static_assert(R == Pair::R && NP <= 2, "PxPair assumes radius 4; level scales below <= 4 levels");
 
   pdl_wait();
   const int b = blockIdx.y;
@@ -297,48 +284,15 @@ lookup_fwd_px_kernel(PyrDev pyr, const float* __restrict__ coords, long long coo
   const float x0 = fetch_coord(coords, coords_bstride, upd, b, hw, pr0 == 0) * coord_scale;
   const long long row = (long long)b * HW + hw;
 
-  float v[NPT][NV];
-  float dxf[NPT], dxc[NPT];
-  int sh[NPT];                      // S - EPL*cs: where the segment starts inside its first chunk (even)
-  int odd[NPT];                     // basef - S - R: 0 or 1 (-1: parked coordinate, everything is zero)
-  int csv[NPT];                     // first chunk of the segment
+  Pair pair[NPT];
 #pragma unroll
   for (int i = 0; i < NPT; ++i) {
     const int pr = pr0 + i;
-    const int lf = 2 * pr;
-    const float lscale = pr == 0 ? 1.0f : 0.25f;
-    int basef, basec;
-    split_coord(x0 * lscale, R, basef, dxf[i]);
-    split_coord(x0 * lscale * 0.5f, R, basec, dxc[i]);
-    const int S = 2 * basec;
-    const int cs = S >> LOG_EPL;
-    sh[i] = S - (cs << LOG_EPL);
-    csv[i] = cs;
-    const int o = basef - S - R;
-    odd[i] = (o == 0 || o == 1) ? o : -1;
-    // (selects instead of pyr.x[lf]: a runtime index would copy the parameter struct to local memory)
-    const int width = (pr == 0 || NP == 1) ? pyr.width[0] : pyr.width[2];
-    const int nchunks = (width + EPL - 1) >> LOG_EPL;
-    const VT* src = static_cast<const VT*>((pr == 0 || NP == 1) ? pyr.ptr[0] : pyr.ptr[2]) +
-                    row * ((pr == 0 || NP == 1) ? pyr.pitch[0] : pyr.pitch[2]) + (long long)cs * EPL;
-#pragma unroll
-    for (int j = 0; j < NCH; ++j) {
-      const int ci = cs + j;
-      float t[EPL];
-#pragma unroll
-      for (int e = 0; e < EPL; ++e) t[e] = 0.f;
-      // the last chunk is only needed when the segment does not start at the chunk boundary
-      const bool need = odd[i] >= 0 && (j < NCH - 1 || sh[i] + SEG > (NCH - 1) * EPL) &&
-                        (unsigned)ci < (unsigned)nchunks;
-      if (need) Vec16<VT>::template load<STREAM>(src + j * EPL, t);
-#pragma unroll
-      for (int e = 0; e < EPL; ++e) v[i][j * EPL + e] = t[e];
-    }
-    if (__builtin_expect((cs + NCH) * EPL > width, 0)) {       // rare: segment reaches the row tail
-#pragma unroll
-      for (int k = 0; k < NV; ++k)
-        if (cs * EPL + k >= width) v[i][k] = 0.f;
-    }
+    // (selects instead of pyr.x[2*pr]: a runtime index would copy the parameter struct to local memory)
+    const bool first = pr == 0 || NP == 1;
+    const VT* fine_row = static_cast<const VT*>(first ? pyr.ptr[0] : pyr.ptr[2]) +
+                         row * (first ? pyr.pitch[0] : pyr.pitch[2]);
+    pair[i].load(fine_row, first ? pyr.width[0] : pyr.width[2], x0 * (pr == 0 ? 1.0f : 0.25f));
   }
   pdl_launch_dependents();
 
@@ -347,32 +301,17 @@ lookup_fwd_px_kernel(PyrDev pyr, const float* __restrict__ coords, long long coo
   for (int i = 0; i < NPT; ++i) {
     const int pr = pr0 + i;
     const int lf = 2 * pr;
+    float e[RD];
     if (2 * pr + 1 < NL) {
-      // coarse level of the pair: pair averages; pc[j] is coarse column cs*EPL/2 + j, columns >= wc
-      // do not exist (negative ones come from chunks that were never loaded: already zero)
-      const int wc = (pr == 0 || NL < 4) ? pyr.width[1] : pyr.width[3];
-      float pc[NV / 2];
-#pragma unroll
-      for (int j = 0; j < NV / 2; ++j) {
-        float a = (v[i][2 * j] + v[i][2 * j + 1]) * 0.5f;
-        if (sizeof(VT) == 2) a = __half2float(__float2half_rn(a));     // stored level is fp16
-        pc[j] = a;
-      }
-      if (__builtin_expect((csv[i] + NCH) * (EPL / 2) > wc, 0)) {
-#pragma unroll
-        for (int j = 0; j < NV / 2; ++j)
-          if (csv[i] * (EPL / 2) + j >= wc) pc[j] = 0.f;
-      }
-      shift_down<NV / 2, LOG_EPL - 1>(pc, sh[i] >> 1);
+      pair[i].template coarse<OT>((pr == 0 || NL < 4) ? pyr.width[1] : pyr.width[3], e);
       OT* d1 = dst + (long long)(lf + 1) * RD * HW;
 #pragma unroll
-      for (int k = 0; k < RD; ++k) d1[(long long)k * HW] = lerp_ref<OT>(pc[k], pc[k + 1], dxc[i]);
+      for (int k = 0; k < RD; ++k) d1[(long long)k * HW] = from_float<OT>(e[k]);
     }
-    // fine level: window starts R + odd elements after the segment start
-    shift_down<NV, LOG_EPL>(v[i], sh[i] + (odd[i] > 0 ? 1 : 0));
+    pair[i].template fine<OT>(e);
     OT* d0 = dst + (long long)lf * RD * HW;
 #pragma unroll
-    for (int k = 0; k < RD; ++k) d0[(long long)k * HW] = lerp_ref<OT>(v[i][R + k], v[i][R + k + 1], dxf[i]);
+    for (int k = 0; k < RD; ++k) d0[(long long)k * HW] = from_float<OT>(e[k]);
   }
 }
 

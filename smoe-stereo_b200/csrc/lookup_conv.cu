@@ -11,8 +11,11 @@
 // (kind::tf32, fp32 accumulate in TMEM), and the epilogue reads TMEM with lane == pixel: for a
 // fixed output channel the 32 lanes of a warp hold 32 consecutive pixels, i.e. one 128-byte line
 // of the channel-major output -- the accumulator layout does the transpose.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
+#include "px_gather.cuh"
 
 namespace smoe {
 
@@ -198,6 +201,141 @@ lookup_conv_kernel(PyrDev pyr, const float* __restrict__ coords, long long coord
   }
 }
 
+// Second version: thread = pixel (PxPair gather, px_gather.cuh).  128 threads per CTA: each thread
+// gathers its pixel's two segments (12 independent 16-byte loads), stages its share of the weights
+// while they are in flight, writes its own operand row (ten conflict-free 16-byte stores into the
+// K-major SWIZZLE_128B tile), one thread issues the MMAs, and the same thread then reads its own
+// TMEM lane (lane == pixel) for the epilogue.  A quarter of the threads and ~3x fewer instructions
+// than the lane-group version, four CTAs per SM instead of two.
+template <typename VT, typename LT, typename CT, int NL, bool STREAM>
+__global__ void __launch_bounds__(kFcPx)
+lookup_conv_px_kernel(PyrDev pyr, const float* __restrict__ coords, long long coords_bstride,
+                      float coord_scale, const float* __restrict__ weight, const float* __restrict__ bias,
+                      int cout, int relu, uint32_t tmem_cols, CT* __restrict__ out, int HW, CoordUpd upd) {
+  using Pair = PxPair<VT, STREAM>;
+  constexpr int RD = Pair::RD;
+  constexpr int NP = (NL + 1) / 2;
+  constexpr int K = NL * RD;                          // input channels of the convolution
+  constexpr int KMMA = (K + 7) / 8 * 8;               // K covered by the MMAs (zero padded)
+  constexpr int KP4 = (KMMA + 3) / 4;                 // 16-byte pieces of an operand row that are read
+  static_assert(KMMA <= kFcKPad && NP <= 2, "K must fit the padded operand");
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ uint32_t s_tmem;
+  __shared__ float s_bias[kFcMaxCout];
+  const uint32_t sA = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;    // swizzle atoms: 1 KiB aligned
+  const uint32_t sB = sA + kFcABytes;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int b = blockIdx.y;
+  const int hw0 = blockIdx.x * kFcPx;
+  const int hw = hw0 + tid;
+  const bool valid = hw < HW;
+
+  if (warp == 0) {
+    ptx::tmem_alloc(ptx::smem_u32(&s_tmem), tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  if (tid == 32) {
+    ptx::mbar_init(ptx::smem_u32(&s_bar), 1);
+    ptx::fence_barrier_init();
+  }
+  pdl_wait();
+  // ---- gather: issue the segment loads of both level pairs first
+  const float x0 = valid ? fetch_coord(coords, coords_bstride, upd, b, hw, true) * coord_scale : 0.f;
+  const long long row = (long long)b * HW + (valid ? hw : 0);
+  Pair pair[NP];
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    const VT* fine_row = static_cast<const VT*>(i == 0 ? pyr.ptr[0] : pyr.ptr[2]) +
+                         row * (i == 0 ? pyr.pitch[0] : pyr.pitch[2]);
+    // an invalid (tail) pixel gathers with a non-finite coordinate: every load is skipped
+    pair[i].load(fine_row, i == 0 ? pyr.width[0] : pyr.width[2],
+                 valid ? x0 * (i == 0 ? 1.0f : 0.25f) : __int_as_float(0x7fc00000));
+  }
+  // ---- weights -> B operand (tf32, zero padded) while the gathers are in flight
+  for (int idx = tid; idx < cout * KP4; idx += kFcPx) {
+    const int n = idx / KP4, piece = idx - n * KP4;
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = piece * 4 + j;
+      w[j] = k < K ? to_tf32(__ldg(weight + (long long)n * K + k)) : 0u;
+    }
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sB + kmajor_off(n, piece * 4, cout)),
+                 "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
+                 : "memory");
+  }
+  for (int c = tid; c < cout; c += kFcPx) s_bias[c] = bias != nullptr ? __ldg(bias + c) : 0.f;
+  // ---- interpolate and write this pixel's operand row (channel = level*RD + tap), zero padded
+  {
+    float row_vals[KP4 * 4];
+#pragma unroll
+    for (int k = 0; k < KP4 * 4; ++k) row_vals[k] = 0.f;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      float e[RD];
+      if (2 * i + 1 < NL) {
+        pair[i].template coarse<LT>((i == 0 || NL < 4) ? pyr.width[1] : pyr.width[3], e);
+#pragma unroll
+        for (int k = 0; k < RD; ++k) row_vals[(2 * i + 1) * RD + k] = e[k];
+      }
+      pair[i].template fine<LT>(e);
+#pragma unroll
+      for (int k = 0; k < RD; ++k) row_vals[2 * i * RD + k] = e[k];
+    }
+#pragma unroll
+    for (int pc = 0; pc < KP4; ++pc)
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sA + kmajor_off(tid, pc * 4, kFcPx)),
+                   "r"(to_tf32(row_vals[4 * pc])), "r"(to_tf32(row_vals[4 * pc + 1])),
+                   "r"(to_tf32(row_vals[4 * pc + 2])), "r"(to_tf32(row_vals[4 * pc + 3]))
+                   : "memory");
+  }
+  pdl_launch_dependents();
+  ptx::fence_proxy_async_smem();          // generic-proxy operand writes -> tensor-core (async) proxy
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem = s_tmem;
+  if (tid == 0) {
+    // c_format f32 | tf32 x tf32 | A, B K-major | N | M
+    const uint32_t idesc = (1u << 4) | (ptx::kFmtTF32 << 7) | (ptx::kFmtTF32 << 10) |
+                           (((uint32_t)cout >> 3) << 17) | ((uint32_t)(kFcPx >> 4) << 24);
+#pragma unroll
+    for (int ks = 0; ks < KMMA / 8; ++ks) {
+      const int atom = (ks * 8) >> 5, kin = (ks * 8) & 31;
+      const uint64_t adesc = ptx::make_smem_desc(sA + atom * kFcPx * 128 + kin * 4, 16, 1024, ptx::kLayoutSwizzle128B);
+      const uint64_t bdesc = ptx::make_smem_desc(sB + atom * cout * 128 + kin * 4, 16, 1024, ptx::kLayoutSwizzle128B);
+      ptx::mma_tf32(tmem, adesc, bdesc, idesc, ks != 0 ? 1u : 0u);
+    }
+    ptx::tc_commit(ptx::smem_u32(&s_bar));
+  }
+  ptx::mbar_wait(ptx::smem_u32(&s_bar), 0);
+  ptx::tc_fence_after_sync();
+  // ---- epilogue: TMEM lane == pixel == thread; every store instruction is one 128-byte line
+  CT* obase = out + (long long)b * cout * HW + hw;
+  for (int c0 = 0; c0 < cout; c0 += 16) {
+    uint32_t acc[16];
+    tmem_ld_32x32_x16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, acc);
+    ptx::tmem_ld_wait();
+    if (valid) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float r = __uint_as_float(acc[j]) + s_bias[c0 + j];
+        if (relu) r = fmaxf(r, 0.f);
+        obase[(long long)(c0 + j) * HW] = from_float<CT>(r);
+      }
+    }
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc(tmem, tmem_cols);
+  }
+}
+
 bool pyramid_vec_ok(const smoe_pyramid_t* p);   // lookup.cu
 
 template <typename VT, typename LT, typename CT>
@@ -211,12 +349,21 @@ static int launch_lookup_conv(const smoe_pyramid_t* pyr, const float* coords, lo
   while ((int)cols < cout) cols <<= 1;
   const bool big = (long long)pyr->B * HW * d.pitch[0] * (long long)sizeof(VT) > (96ll << 20);
   dim3 grid((HW + kFcPx - 1) / kFcPx, pyr->B);
+  // SMOE_CORR_LOOKUP_CONV=lanes selects the first (lane-group) version
+  static const bool lanes = [] { const char* e = getenv("SMOE_CORR_LOOKUP_CONV"); return e && e[0] == 'l'; }();
 #define SMOE_FC_LAUNCH(NLV, STREAMV)                                                              \
   do {                                                                                            \
-    auto kern = lookup_conv_kernel<VT, LT, CT, NLV, STREAMV>;                                     \
-    SMOE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    SMOE_CUDA_OK(launch_kernel(kern, grid, dim3(kFcThreads), smem, st, d, coords, cbs, cs, weight, \
-                               bias, cout, relu, cols, static_cast<CT*>(out), HW, upd));          \
+    if (lanes) {                                                                                  \
+      auto kern = lookup_conv_kernel<VT, LT, CT, NLV, STREAMV>;                                   \
+      SMOE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      SMOE_CUDA_OK(launch_kernel(kern, grid, dim3(kFcThreads), smem, st, d, coords, cbs, cs, weight, \
+                                 bias, cout, relu, cols, static_cast<CT*>(out), HW, upd));        \
+    } else {                                                                                      \
+      auto kern = lookup_conv_px_kernel<VT, LT, CT, NLV, STREAMV>;                                \
+      SMOE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      SMOE_CUDA_OK(launch_kernel_pdl(kern, grid, dim3(kFcPx), smem, st, d, coords, cbs, cs, weight, \
+                                     bias, cout, relu, cols, static_cast<CT*>(out), HW, upd));    \
+    }                                                                                             \
   } while (0)
 #define SMOE_FC_LEVELS(STREAMV)                                                                   \
   switch (pyr->num_levels) {                                                                      \
