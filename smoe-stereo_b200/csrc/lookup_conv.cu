@@ -254,18 +254,37 @@ lookup_conv_px_kernel(PyrDev pyr, const float* __restrict__ coords, long long co
     pair[i].load(fine_row, i == 0 ? pyr.width[0] : pyr.width[2],
                  valid ? x0 * (i == 0 ? 1.0f : 0.25f) : __int_as_float(0x7fc00000));
   }
-  // ---- weights -> B operand (tf32, zero padded) while the gathers are in flight
-  for (int idx = tid; idx < cout * KP4; idx += kFcPx) {
-    const int n = idx / KP4, piece = idx - n * KP4;
-    uint32_t w[4];
+  // ---- weights -> B operand (tf32, zero padded) while the gathers are in flight.  Row n of the
+  // weights is K contiguous floats; thread (n = idx / KP4, piece) handles one 16-byte piece.  All
+  // loads of a thread are issued before the first is used (cout = 64: 5 pieces per thread).
+  {
+    constexpr int kMaxPieces = (kFcMaxCout * KP4 + kFcPx - 1) / kFcPx;
+    const int total = cout * KP4;
+#pragma unroll 1
+    for (int i0 = 0; i0 < kMaxPieces; i0 += 5) {
+      float wv[5][4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int k = piece * 4 + j;
-      w[j] = k < K ? to_tf32(__ldg(weight + (long long)n * K + k)) : 0u;
+      for (int u = 0; u < 5; ++u) {
+        const int idx = tid + (i0 + u) * kFcPx;
+        const int n = idx / KP4, piece = idx - n * KP4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = piece * 4 + j;
+          wv[u][j] = (idx < total && k < K) ? __ldg(weight + (long long)n * K + k) : 0.f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 5; ++u) {
+        const int idx = tid + (i0 + u) * kFcPx;
+        const int n = idx / KP4, piece = idx - n * KP4;
+        if (idx < total)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sB + kmajor_off(n, piece * 4, cout)),
+                       "r"(to_tf32(wv[u][0])), "r"(to_tf32(wv[u][1])), "r"(to_tf32(wv[u][2])),
+                       "r"(to_tf32(wv[u][3]))
+                       : "memory");
+      }
+      if (tid + (i0 + 5) * kFcPx >= total) break;
     }
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sB + kmajor_off(n, piece * 4, cout)),
-                 "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
-                 : "memory");
   }
   for (int c = tid; c < cout; c += kFcPx) s_bias[c] = bias != nullptr ? __ldg(bias + c) : 0.f;
   // ---- interpolate and write this pixel's operand row (channel = level*RD + tap), zero padded
@@ -349,8 +368,15 @@ static int launch_lookup_conv(const smoe_pyramid_t* pyr, const float* coords, lo
   while ((int)cols < cout) cols <<= 1;
   const bool big = (long long)pyr->B * HW * d.pitch[0] * (long long)sizeof(VT) > (96ll << 20);
   dim3 grid((HW + kFcPx - 1) / kFcPx, pyr->B);
-  // SMOE_CORR_LOOKUP_CONV=lanes selects the first (lane-group) version
-  static const bool lanes = [] { const char* e = getenv("SMOE_CORR_LOOKUP_CONV"); return e && e[0] == 'l'; }();
+  // SMOE_CORR_LOOKUP_CONV=lanes|px forces one version.  Default: thread-per-pixel (cfg1 8.98 -> 6.35 us,
+  // fp16 volumes 10.7 -> 6.4 us and 72 -> 57 us at B=8 96x312), except fp32 volumes beyond L2, where
+  // the lane-group version still measures ~15% faster (66 vs 78 us): both are latency-bound there
+  // (4 CTAs per SM, serial gather -> MMA -> epilogue chain; profiles/r01/README.md).
+  static const int forced = [] {
+    const char* e = getenv("SMOE_CORR_LOOKUP_CONV");
+    return !e ? 0 : (e[0] == 'l' ? 1 : 2);
+  }();
+  const bool lanes = forced == 1 || (forced == 0 && big && sizeof(VT) == 4);
 #define SMOE_FC_LAUNCH(NLV, STREAMV)                                                              \
   do {                                                                                            \
     if (lanes) {                                                                                  \
