@@ -23,11 +23,15 @@ for name in (sys.argv[1:] or ["cfg1", "cfg2", "cfg3", "cfg4"]):
         res = {}
         for which, kn in ((3, "vec"), (2, "pair"), (1, "px")):
             L.smoe_corr_debug_set_lookup_kernel(which)
-            def lk():
+            keep_all = os.environ.get("PROBE_KEEP") is not None   # 32 distinct output buffers (as bench.py):
+            def lk():                                              # writes stream to DRAM instead of staying in L2
+                outs = []
                 o = None
                 for t in range(32):
                     o = _lookup(pyr, coords[t % 8], 4, dt)
-                return o
+                    if keep_all:
+                        outs.append(o)
+                return outs if keep_all else o
             gr = torch.cuda.CUDAGraph()
             with torch.cuda.stream(side):
                 lk(); torch.cuda.synchronize()
