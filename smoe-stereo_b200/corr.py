@@ -116,6 +116,9 @@ class FusedPyramid:
         self.c.dtype = _DTYPE_CODE[dtype]
         self.c.B, self.c.H, self.c.W1 = B, H, W1
         self.ref = ctypes.byref(self.c)
+        # cached for the eager per-call path (_lookup): device ordinal, coords plane geometry
+        self.dev_idx = device.index if device.index is not None else _raw_device()
+        self._coords_fast = (H * W1, W1, 1)          # strides (ch, H, W) of a contiguous coords tensor
 
     def level(self, i: int) -> torch.Tensor:
         """Strided (B,H,W1,W2_i) view of level i (no copy)."""
@@ -264,15 +267,28 @@ _lookup_fn = None
 
 
 def _lookup(pyr: FusedPyramid, coords: torch.Tensor, radius: int, out_dtype) -> torch.Tensor:
+    """One eager lookup.  This is the call an unmodified model makes once per GRU iteration, so the
+    host side is kept short (tools/eager_overhead.py): a contiguous fp32 CUDA coords tensor of the
+    right shape skips the general validation, the device switch and the stream wrapper objects."""
     global _lookup_fn
     if _lookup_fn is None:
         _lookup_fn = _lib.lib().smoe_corr_lookup
-    coords, bstride = _coords_plane(coords, pyr.B, pyr.H, pyr.W1)
+    shp = coords.shape
+    if (coords.dtype is torch.float32 and coords.is_cuda and len(shp) == 4 and shp[0] == pyr.B
+            and shp[2] == pyr.H and shp[3] == pyr.W1 and coords.stride()[1:] == pyr._coords_fast):
+        bstride = coords.stride(0) if pyr.B > 1 else shp[1] * pyr.H * pyr.W1
+    else:
+        coords, bstride = _coords_plane(coords, pyr.B, pyr.H, pyr.W1)
     out = torch.empty((pyr.B, pyr.num_levels * (2 * radius + 1), pyr.H, pyr.W1), dtype=out_dtype,
                       device=pyr.device)
-    with _on_device(pyr.device):
+    idx = pyr.dev_idx
+    if _raw_stream is not None and _raw_device() == idx:
         rc = _lookup_fn(pyr.ref, coords.data_ptr(), bstride, 1.0, radius, out.data_ptr(),
-                        _DTYPE_CODE[out_dtype], _stream_ptr(pyr.device))
+                        _DTYPE_CODE[out_dtype], _raw_stream(idx))
+    else:
+        with _on_device(pyr.device):
+            rc = _lookup_fn(pyr.ref, coords.data_ptr(), bstride, 1.0, radius, out.data_ptr(),
+                            _DTYPE_CODE[out_dtype], _stream_ptr(pyr.device))
     if rc:
         _lib.check(rc, "smoe_corr_lookup")
     return out
