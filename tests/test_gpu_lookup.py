@@ -163,3 +163,34 @@ def test_thread_per_pixel_kernel_equals_lane_group_kernels_bitwise(sb, dtype, le
             assert torch.equal(outs["px"][t], outs["vec"][t]), (B, C, H, W1, W2, t)
             assert torch.equal(outs["pair"][t], outs["vec"][t])     # (pair falls through to vec for 1/3 levels)
             assert torch.isfinite(outs["px"][t]).all()
+
+
+def test_kitti_cfg3_full_size_streaming_lookup_vs_oracle(sb, oracle):
+    """BASELINE config 3 at full size (KITTI 384x1248: B=8, 96x312; 583 MB pyramid, far beyond L2):
+    the streaming variant of the thread-per-pixel kernel (64-byte fills, one thread per level pair)
+    against the oracle's lookup on the very pyramid the build wrote, three build rows against the
+    oracle's volume, and the channels-last build against the NCHW build bit for bit."""
+    from gpu_util import dev, make_coords
+    from conftest import rel_max as rmax
+    B, C, H, W = 8, 256, 96, 312
+    g = torch.Generator(device="cpu").manual_seed(21)
+    f1 = torch.randn(B, C, H, W, generator=g).to(dev())
+    f2 = torch.randn(B, C, H, W, generator=g).to(dev())
+    blk = sb.CorrBlock1D(f1, f2)
+    pyr = blk._state.pyr
+    assert pyr.buffer.numel() * 4 > (512 << 20)
+    for (b, h) in ((0, 0), (3, 50), (7, 95)):
+        want = oracle.c_pyramid(oracle.c_corr_volume(f1[b:b + 1, :, h:h + 1].cpu().numpy().copy(),
+                                                     f2[b:b + 1, :, h:h + 1].cpu().numpy().copy()), 4)
+        for i in range(4):
+            assert rmax(pyr.level(i)[b:b + 1, h:h + 1].cpu().numpy(), want[i]) < 1e-3
+    levels = [np.ascontiguousarray(pyr.level(i).cpu().numpy()) for i in range(4)]
+    coords = make_coords(B, H, W, W, 2, seed=17)
+    for t in range(2):
+        got = blk(torch.from_numpy(coords[t]).to(dev())).cpu().numpy()
+        want = oracle.c_lookup(levels, np.ascontiguousarray(coords[t]), 4)
+        assert rmax(got, want) < ORACLE_TOL
+    cl = sb.CorrBlock1D(f1.contiguous(memory_format=torch.channels_last),
+                        f2.contiguous(memory_format=torch.channels_last))
+    for i in range(4):
+        assert torch.equal(cl._state.pyr.level(i), pyr.level(i))
