@@ -1,15 +1,20 @@
 // lookup.cu -- pyramid lookup (forward), lookup backward and pyramid-gradient fold for sm_100a.
 //
-// These kernels are HBM/L2-bound gathers and scatters, not GEMMs.  Design (DESIGN.md section 4):
-//  * forward, vector path: a group of 4 lanes owns one pixel; each lane fetches ONE aligned
-//    16-byte chunk of the (2r+2)-tap window of each level (all levels issued before any is
-//    used => 4 independent 16-B loads in flight per lane), neighbours exchange the chunk
-//    boundary value with one warp shuffle, interpolate, and the CTA transposes the 32-pixel x
-//    L*(2r+1) tile through shared memory so every global store is a full 128-byte line of one
-//    output channel (the output is channel-major, core/corr.py:146).
-//  * backward, accumulate: the mirror image -- the gradient tile is staged through shared
-//    memory with coalesced loads and each lane read-modify-writes the one 16-byte chunk it owns;
-//    rows are pixel-private, so no atomics are needed (as in sampler_kernel.cu:102).
+// These kernels are HBM/L2-bound gathers and scatters, not GEMMs.  Design (DESIGN.md section 3):
+//  * forward, default: lookup_fwd_px_kernel -- ONE thread per pixel (or per level pair of a
+//    pixel) gathers two contiguous segments (levels 0 and 2; levels 1 and 3 are recomputed
+//    bit-exactly) with twelve 16-byte loads issued up front, applies the data-dependent window
+//    start with a register select network and stores every output channel as one coalesced
+//    128-byte line per warp straight from registers (px_gather.cuh).
+//  * forward, lane-group kernels (lookup_fwd_vec_kernel: 4 lanes per pixel, four windows;
+//    lookup_fwd_pair_kernel: 8 lanes per pixel, two segments): the earlier designs, kept as
+//    bit-exact cross-checks behind smoe_corr_debug_set_lookup_kernel; 3.3x more instructions.
+//  * backward, batched (default for training): lookup_bwd_lvl_kernel -- warp = level, lane =
+//    pixel, the gradient rows of a 32-pixel tile live in shared memory, all iterations of a step
+//    stream through registers, the fold runs in shared memory, level 0 is written once.
+//  * backward, accumulate (per call): the gradient tile is staged through shared memory with
+//    coalesced loads and each lane read-modify-writes the one 16-byte chunk it owns; rows are
+//    pixel-private, so no atomics are needed (as in sampler_kernel.cu:102).
 //  * backward, overwrite: one pass writes every element of the dense gradient (zeros outside the
 //    window), replacing the reference's zeros_like + scatter pair (sampler_kernel.cu:148-163).
 //  * generic scalar kernels cover unaligned widths / pitches and radii other than 4.
