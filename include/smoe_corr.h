@@ -72,6 +72,13 @@ extern "C" {
                                       Needs C*sizeof(T) % 16 == 0; no constraint on W1/W2 and no
                                       workspace.                                                   */
 
+#define SMOE_BUILD_SKIP_ODD_LEVELS 4 /* do not write levels 1 and 3.  The radius-4 lookup kernels read
+                                      levels 0 and 2 only (level i+1 is the pair average of level i
+                                      and is recomputed on the fly, bit-exactly), so a third of the
+                                      pyramid bytes never has to reach memory.  The caller then sets
+                                      levels_missing = 0b1010 (masked to num_levels) in the pyramids
+                                      it passes to smoe_corr_lookup*.                              */
+
 /* smoe_corr_lookup_bwd modes */
 #define SMOE_BWD_OVERWRITE 0     /* write every element of the gradient (zeros outside the taps):
                                     == zeros_like + scatter of sampler_kernel.cu:148-163         */
@@ -86,7 +93,10 @@ typedef struct smoe_pyramid {
   int32_t num_levels;                   /* 1..SMOE_MAX_LEVELS                                */
   int32_t dtype;                        /* SMOE_DTYPE_*                                      */
   int32_t B, H, W1;                     /* pixel rows = B*H*W1                               */
-  int32_t reserved;
+  int32_t levels_missing;               /* bit i set: level i holds no data (it was skipped by
+                                           smoe_corr_build(SMOE_BUILD_SKIP_ODD_LEVELS)); entry
+                                           points that would read it return SMOE_ERR_INVALID_ARG.
+                                           0 = every level is present                        */
 } smoe_pyramid_t;
 
 /* ABI version of the loaded library (== SMOE_CORR_ABI_VERSION). */

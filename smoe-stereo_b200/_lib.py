@@ -18,6 +18,7 @@ OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_CUDA = 0, 1, 2, 3
 DTYPE_F32, DTYPE_F16 = 0, 1
 BUILD_TF32_TRUNCATE = 1
 BUILD_CHANNELS_LAST = 2
+BUILD_SKIP_ODD_LEVELS = 4
 BWD_OVERWRITE, BWD_ACCUMULATE = 0, 1
 MAX_BATCHED_ITERS = 48
 
@@ -42,7 +43,7 @@ class Pyramid(ctypes.Structure):
         ("B", ctypes.c_int32),
         ("H", ctypes.c_int32),
         ("W1", ctypes.c_int32),
-        ("reserved", ctypes.c_int32),
+        ("levels_missing", ctypes.c_int32),
     ]
 
 

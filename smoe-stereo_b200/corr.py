@@ -43,6 +43,12 @@ _default_volume_dtype = torch.float16 if os.environ.get("SMOE_CORR_VOLUME_DTYPE"
     "fp16", "float16", "half") else None
 
 
+# SMOE_CORR_ALL_LEVELS=1: always write all four pyramid levels; =0: never write levels 1 and 3 for
+# radius-4 blocks; default: skip them only for volumes beyond L2 (see _CorrBlockBase.__init__)
+_skip_odd_levels = {"": None, "0": True, "1": False}.get(os.environ.get("SMOE_CORR_ALL_LEVELS", ""), None)
+_SKIP_ODD_MIN_BYTES = 96 << 20      # None above: skip levels 1/3 only for volumes beyond L2
+
+
 def set_default_volume_dtype(dtype) -> None:
     """None / torch.float32 -> fp32 pyramids (default); torch.float16 -> fp16 storage (see above)."""
     global _default_volume_dtype
@@ -115,6 +121,7 @@ class FusedPyramid:
         self.c.num_levels = num_levels
         self.c.dtype = _DTYPE_CODE[dtype]
         self.c.B, self.c.H, self.c.W1 = B, H, W1
+        self.c.levels_missing = 0
         self.ref = ctypes.byref(self.c)
         # cached for the eager per-call path (_lookup): device ordinal, coords plane geometry
         self.dev_idx = device.index if device.index is not None else _raw_device()
@@ -122,8 +129,32 @@ class FusedPyramid:
 
     def level(self, i: int) -> torch.Tensor:
         """Strided (B,H,W1,W2_i) view of level i (no copy)."""
+        if (self.c.levels_missing >> i) & 1:
+            self.materialize()
+        return self._level_view(i)
+
+    def _level_view(self, i: int) -> torch.Tensor:
         v = self.buffer[:, self.offsets[i]:self.offsets[i] + self.widths[i]]
         return v.view(self.B, self.H, self.W1, self.widths[i])
+
+    def mark_missing(self, mask: int) -> None:
+        """Levels the build did not write (SMOE_BUILD_SKIP_ODD_LEVELS)."""
+        self.c.levels_missing = mask & ((1 << self.num_levels) - 1)
+
+    def materialize(self) -> None:
+        """Fill in the levels the build skipped: level i = pair average of level i-1, with the very
+        arithmetic of the build epilogue / F.avg_pool2d (fp32 sum, * 0.5, one rounding), so the
+        result is bit-identical to a build without SMOE_BUILD_SKIP_ODD_LEVELS.  Only needed by
+        consumers other than the radius-4 lookup kernels (`corr_pyramid`, cross-check kernels)."""
+        missing = self.c.levels_missing
+        for i in range(1, self.num_levels):
+            if (missing >> i) & 1:
+                w = self.widths[i]
+                prev = self._level_view(i - 1)
+                if w > 0:
+                    avg = (prev[..., 0:2 * w:2].float() + prev[..., 1:2 * w:2].float()) * 0.5
+                    self._level_view(i).copy_(avg.to(self.dtype))
+        self.c.levels_missing = 0
 
 
 def _is_channels_last(t: torch.Tensor) -> bool:
@@ -162,6 +193,7 @@ def _build_into(pyr: FusedPyramid, fmap1: torch.Tensor, fmap2: torch.Tensor, fla
         raise RuntimeError("feature maps must be contiguous (NCHW or channels-last)")
     ws_bytes = 0 if flags & _lib.BUILD_CHANNELS_LAST else \
         L.smoe_corr_build_workspace_bytes(B, C, H, W1, W2, code)
+    pyr.mark_missing(0b1010 if flags & _lib.BUILD_SKIP_ODD_LEVELS else 0)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=fmap1.device) if ws_bytes else None
     with _on_device(fmap1.device):
         rc = L.smoe_corr_build(fmap1.data_ptr(), fmap2.data_ptr(), code, B, C, H, W1, W2, pyr.ref,
@@ -303,6 +335,7 @@ class _State:
         self.grad_pyr: FusedPyramid | None = None      # per-call (accumulating) backward path
         self.pending: list = []                        # deferred lookup backwards (batched path)
         self.radius = 4
+        self.build_flags = 0
 
 
 class _BuildFn(torch.autograd.Function):
@@ -314,7 +347,7 @@ class _BuildFn(torch.autograd.Function):
     def forward(ctx, fmap1, fmap2, state):
         pyr = FusedPyramid(fmap1.shape[0], fmap1.shape[2], fmap1.shape[3], fmap2.shape[3],
                            state.num_levels, state.pyr_dtype, fmap1.device)
-        _build_into(pyr, fmap1, fmap2)
+        _build_into(pyr, fmap1, fmap2, state.build_flags)
         state.pyr = pyr
         ctx.state = state
         ctx.save_for_backward(fmap1, fmap2)
@@ -399,6 +432,18 @@ class _CorrBlockBase:
         if self._float_output and fmap1.dtype == torch.float32 and _default_volume_dtype is not None:
             pyr_dtype = _default_volume_dtype
         st.num_levels, st.radius, st.pyr_dtype = num_levels, radius, pyr_dtype
+        # The radius-4 lookup kernels read levels 0 and 2 only and recompute 1 and 3 (bit-exactly),
+        # so for volumes that stream through DRAM the build does not write them (a third of the
+        # pyramid bytes: cfg3 build 208 -> 191 us).  `corr_pyramid` and the cross-check kernels
+        # materialise them on demand (FusedPyramid.materialize).  L2-resident volumes keep all
+        # levels: there the shorter build was offset by slower first lookups (149 vs 145 us per
+        # cfg1 step, tools/step_probe.py).
+        st.build_flags = 0
+        if radius == 4 and _skip_odd_levels is not False:
+            vol_bytes = (fmap1.shape[0] * fmap1.shape[2] * fmap1.shape[3] * fmap2.shape[3] * 15 // 8
+                         * (2 if pyr_dtype == torch.float16 else 4))
+            if _skip_odd_levels is True or vol_bytes > _SKIP_ODD_MIN_BYTES:
+                st.build_flags = _lib.BUILD_SKIP_ODD_LEVELS
         self._state = st
         self._token = None
         if torch.is_grad_enabled() and (fmap1.requires_grad or fmap2.requires_grad):
@@ -406,7 +451,7 @@ class _CorrBlockBase:
         else:
             st.pyr = FusedPyramid(fmap1.shape[0], fmap1.shape[2], fmap1.shape[3], fmap2.shape[3],
                                   num_levels, pyr_dtype, fmap1.device)
-            _build_into(st.pyr, fmap1, fmap2)
+            _build_into(st.pyr, fmap1, fmap2, st.build_flags)
 
     @property
     def corr_pyramid(self):
@@ -501,6 +546,8 @@ class _CorrBlockBase:
             y = F.conv2d(corr, w4, bias.to(corr.dtype) if bias is not None else None)
             return (F.relu(y) if relu else y).to(out_dtype)
         _require_cuda(weight2d, "weight")
+        if p.c.levels_missing and p.dtype == torch.float32:
+            p.materialize()      # fp32 volumes beyond L2 run the lane-group version, which reads all levels
         w = weight2d.detach().to(torch.float32).contiguous()
         bvec = bias.detach().to(torch.float32).contiguous() if bias is not None else None
         coords, bstride = _coords_plane(coords, p.B, p.H, p.W1)

@@ -90,6 +90,7 @@ struct BuildDims {
   int stage_bytes;           // one N tile needs), sized to fill shared memory
   int pair;                  // CTA-pair kernel (MT counts 256-row tiles)
   int kmajor;                // channels-last feature maps (SMOE_BUILD_CHANNELS_LAST)
+  int store_mask;            // bit i: level i is written (SMOE_BUILD_SKIP_ODD_LEVELS clears 1 and 3)
   int debug;                 // probe builds only (kProbes)
 };
 
@@ -178,29 +179,35 @@ template <typename OT> struct ChunkStage;
 
 template <> struct ChunkStage<float> {
   static constexpr int kSubChunks = 1;     // 32 fp32 columns == 128 bytes
+  // store_mask: bit i set = level i is staged and stored (SMOE_BUILD_SKIP_ODD_LEVELS clears 1 and 3;
+  // a skipped level is still computed when a finer stored level is pooled from it)
   template <bool>
   __device__ static void run(const uint32_t (&acc)[32], uint32_t stg, int row, int /*sub*/,
-                             const Scaler& sc, int num_levels, const GroupPlan& gp) {
+                             const Scaler& sc, int num_levels, const GroupPlan& gp, int store_mask) {
     float v[32];
     sc.apply(acc, v);
 #pragma unroll
     for (int g = 0; g < 8; ++g)
       st_shared_v4(stg_addr(stg, 0, row, 16 * g), v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
-    if (num_levels < 2) return;
+    if (num_levels < 2 || (store_mask >> 1) == 0) return;
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = (v[2 * j] + v[2 * j + 1]) * 0.5f;
+    if (store_mask & 2) {
 #pragma unroll
-    for (int g = 0; g < 4; ++g)
-      st_shared_v4(stg_addr(stg + kStgLevelBytes, gp.d[1], row, gp.off[1] + 16 * g), v[4 * g], v[4 * g + 1],
-                   v[4 * g + 2], v[4 * g + 3]);
-    if (num_levels < 3) return;
+      for (int g = 0; g < 4; ++g)
+        st_shared_v4(stg_addr(stg + kStgLevelBytes, gp.d[1], row, gp.off[1] + 16 * g), v[4 * g], v[4 * g + 1],
+                     v[4 * g + 2], v[4 * g + 3]);
+    }
+    if (num_levels < 3 || (store_mask >> 2) == 0) return;
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = (v[2 * j] + v[2 * j + 1]) * 0.5f;
+    if (store_mask & 4) {
 #pragma unroll
-    for (int g = 0; g < 2; ++g)
-      st_shared_v4(stg_addr(stg + 2 * kStgLevelBytes, gp.d[2], row, gp.off[2] + 16 * g), v[4 * g],
-                   v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
-    if (num_levels < 4) return;
+      for (int g = 0; g < 2; ++g)
+        st_shared_v4(stg_addr(stg + 2 * kStgLevelBytes, gp.d[2], row, gp.off[2] + 16 * g), v[4 * g],
+                     v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+    }
+    if (num_levels < 4 || (store_mask & 8) == 0) return;
 #pragma unroll
     for (int j = 0; j < 4; ++j) v[j] = (v[2 * j] + v[2 * j + 1]) * 0.5f;
     st_shared_v4(stg_addr(stg + 3 * kStgLevelBytes, gp.d[3], row, gp.off[3]), v[0], v[1], v[2], v[3]);
@@ -228,7 +235,7 @@ template <> struct ChunkStage<__half> {
   // opted into by the caller) the fp32 quotient is rounded once.
   template <bool kEinsumIsHalf>
   __device__ static void run(const uint32_t (&acc)[32], uint32_t stg, int row, int sub,
-                             const Scaler& sc, int num_levels, const GroupPlan& gp) {
+                             const Scaler& sc, int num_levels, const GroupPlan& gp, int store_mask) {
     __half2 h0[16];
     if (!kEinsumIsHalf) {
 #pragma unroll
@@ -254,19 +261,22 @@ template <> struct ChunkStage<__half> {
     for (int g = 0; g < 4; ++g)
       st_shared_v4u(stg_addr(stg, 0, row, 64 * sub + 16 * g), as_u32(h0[4 * g]), as_u32(h0[4 * g + 1]),
                     as_u32(h0[4 * g + 2]), as_u32(h0[4 * g + 3]));
-    if (num_levels < 2) return;
+    if (num_levels < 2 || (store_mask >> 1) == 0) return;
     __half2 h1[8];
     pool<8>(h0, h1);
+    if (store_mask & 2) {
 #pragma unroll
-    for (int g = 0; g < 2; ++g)
-      st_shared_v4u(stg_addr(stg + kStgLevelBytes, gp.d[1], row, gp.off[1] + 32 * sub + 16 * g), as_u32(h1[4 * g]), as_u32(h1[4 * g + 1]),
-                    as_u32(h1[4 * g + 2]), as_u32(h1[4 * g + 3]));
-    if (num_levels < 3) return;
+      for (int g = 0; g < 2; ++g)
+        st_shared_v4u(stg_addr(stg + kStgLevelBytes, gp.d[1], row, gp.off[1] + 32 * sub + 16 * g), as_u32(h1[4 * g]), as_u32(h1[4 * g + 1]),
+                      as_u32(h1[4 * g + 2]), as_u32(h1[4 * g + 3]));
+    }
+    if (num_levels < 3 || (store_mask >> 2) == 0) return;
     __half2 h2[4];
     pool<4>(h1, h2);
-    st_shared_v4u(stg_addr(stg + 2 * kStgLevelBytes, gp.d[2], row, gp.off[2] + 16 * sub), as_u32(h2[0]), as_u32(h2[1]), as_u32(h2[2]),
-                  as_u32(h2[3]));
-    if (num_levels < 4) return;
+    if (store_mask & 4)
+      st_shared_v4u(stg_addr(stg + 2 * kStgLevelBytes, gp.d[2], row, gp.off[2] + 16 * sub), as_u32(h2[0]), as_u32(h2[1]), as_u32(h2[2]),
+                    as_u32(h2[3]));
+    if (num_levels < 4 || (store_mask & 8) == 0) return;
     __half2 h3[2];
     pool<2>(h2, h3);
     st_shared_v2u(stg_addr(stg + 3 * kStgLevelBytes, gp.d[3], row, gp.off[3] + 8 * sub), as_u32(h3[0]), as_u32(h3[1]));
@@ -533,7 +543,8 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             ptx::tmem_ld_32x32(taddr + c * kChunkCols + sub * 32, acc);
             ptx::tmem_ld_wait();
             if (kProbes && sub == 0) t2 = clock64();
-            ChunkStage<OT>::template run<sizeof(IT) == 2>(acc, stg_base, lane, sub, sc, num_levels, gp);
+            ChunkStage<OT>::template run<sizeof(IT) == 2>(acc, stg_base, lane, sub, sc, num_levels, gp,
+                                                          dims.store_mask);
           }
         }
         __syncwarp();                                // staged tiles visible to the whole warp
@@ -544,7 +555,7 @@ corr_build_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           const long long grow = (long long)bh * dims.W1 + m0;
 #pragma unroll
           for (int i = 0; i < SMOE_MAX_LEVELS; ++i)
-            if (i < num_levels && gp.flush[i])
+            if (i < num_levels && gp.flush[i] && ((dims.store_mask >> i) & 1))
               store_staged_tile<OT>(stg_base + i * kStgLevelBytes, i == 0 ? 0 : gp.d[i],
                                     static_cast<OT*>(out.ptr[i]) + grow * out.pitch[i], out.pitch[i],
                                     (n0 + gp.first[i] * kChunkCols) >> i, out.width[i], rows_valid, lane);
@@ -790,6 +801,7 @@ int smoe_corr_build(const void* fmap1, const void* fmap2, int in_dtype, int B, i
   BuildDims dims;
   dims.W1 = W1; dims.W2 = W2; dims.C = C; dims.H = H; dims.BH = B * H;
   dims.kmajor = kmajor ? 1 : 0;
+  dims.store_mask = (flags & SMOE_BUILD_SKIP_ODD_LEVELS) ? 0x5 : 0xF;
   {
     const char* e = getenv("SMOE_CORR_BUILD_PAIR");
     dims.pair = (e && !kmajor) ? atoi(e) : 0;

@@ -1064,6 +1064,16 @@ static int lookup_impl(const smoe_pyramid_t* pyr, const float* coords, int64_t c
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const PyrDev d = to_dev(pyr);
   const bool f16v = pyr->dtype == SMOE_DTYPE_F16, f16o = out_dtype == SMOE_DTYPE_F16;
+  if (pyr->levels_missing & ((1 << pyr->num_levels) - 1)) {
+    // levels skipped by the build (SMOE_BUILD_SKIP_ODD_LEVELS): only the thread-per-pixel kernel,
+    // which reads levels 0 and 2 and recomputes 1 and 3, can serve the lookup
+    SMOE_REQUIRE((pyr->levels_missing & 0x5) == 0, SMOE_ERR_INVALID_ARG,
+                 "lookup: an even level is marked missing (levels_missing=0x%x)", pyr->levels_missing);
+    SMOE_REQUIRE(radius == 4 && pyramid_vec_ok(pyr) && (g_fwd_kernel == 0 || g_fwd_kernel == 1),
+                 SMOE_ERR_INVALID_ARG,
+                 "lookup: levels 0x%x of the pyramid were not built; radius %d / this kernel choice "
+                 "needs them (build without SMOE_BUILD_SKIP_ODD_LEVELS)", pyr->levels_missing, radius);
+  }
   if (radius == 4 && pyramid_vec_ok(pyr)) {
     if (!f16v)
       dispatch_fwd_vec<float, float>(pyr->num_levels, d, coords, coords_batch_stride, coord_scale,

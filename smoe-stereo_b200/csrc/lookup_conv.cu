@@ -376,7 +376,10 @@ static int launch_lookup_conv(const smoe_pyramid_t* pyr, const float* coords, lo
     const char* e = getenv("SMOE_CORR_LOOKUP_CONV");
     return !e ? 0 : (e[0] == 'l' ? 1 : 2);
   }();
-  const bool lanes = forced == 1 || (forced == 0 && big && sizeof(VT) == 4);
+  const bool missing = (pyr->levels_missing & ((1 << pyr->num_levels) - 1)) != 0;   // odd levels not built
+  SMOE_REQUIRE(!(missing && forced == 1) && (pyr->levels_missing & 0x5) == 0, SMOE_ERR_INVALID_ARG,
+               "lookup_conv1x1: levels 0x%x of the pyramid were not built", pyr->levels_missing);
+  const bool lanes = !missing && (forced == 1 || (forced == 0 && big && sizeof(VT) == 4));
 #define SMOE_FC_LAUNCH(NLV, STREAMV)                                                              \
   do {                                                                                            \
     if (lanes) {                                                                                  \

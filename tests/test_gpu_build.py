@@ -115,11 +115,10 @@ def test_build_batch_independent_and_deterministic(sb):
     g = torch.Generator(device="cpu").manual_seed(0)
     f1 = torch.randn(3, 64, 5, 96, generator=g).to(dev())
     f2 = torch.randn(3, 64, 5, 96, generator=g).to(dev())
-    full = sb.CorrBlock1D(f1, f2)._state.pyr.buffer.clone()
-    again = sb.CorrBlock1D(f1, f2)._state.pyr.buffer
-    rows = 5 * 96
-    for i in range(4):
-        pass
+    p_full, p_again = sb.CorrBlock1D(f1, f2)._state.pyr, sb.CorrBlock1D(f1, f2)._state.pyr
+    for p_ in (p_full, p_again):
+        p_.materialize()                    # levels 1/3 are skipped by the block's build
+    full, again = p_full.buffer.clone(), p_again.buffer
     pyr = sb.CorrBlock1D(f1, f2)._state.pyr
     for b in range(3):
         one = sb.CorrBlock1D(f1[b:b + 1].contiguous(), f2[b:b + 1].contiguous())._state.pyr
@@ -287,3 +286,42 @@ def test_build_channels_last_backward(sb):
         grads.append((a.grad.clone(), b.grad.clone()))
     for k in range(2):
         assert rel_max(grads[1][k].cpu().numpy(), grads[0][k].cpu().numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+@pytest.mark.parametrize("shape", [(1, 64, 6, 240, 240), (2, 32, 3, 77, 85), (1, 32, 2, 40, 9)])
+def test_build_skip_odd_levels_equals_full_build(sb, shape, dtype):
+    """SMOE_BUILD_SKIP_ODD_LEVELS: levels 0 and 2 are bit-identical to a full build, levels 1 and 3
+    are left untouched by the kernel, and FusedPyramid.materialize() reproduces them bit for bit."""
+    from gpu_util import dev
+    from smoe_stereo_b200 import _lib
+    from smoe_stereo_b200.corr import _build_into
+    B, C, H, W1, W2 = shape
+    g = torch.Generator(device="cpu").manual_seed(W2)
+    f1 = torch.randn(B, C, H, W1, generator=g).to(dev()).to(dtype)
+    f2 = torch.randn(B, C, H, W2, generator=g).to(dev()).to(dtype)
+    full = sb.FusedPyramid(B, H, W1, W2, 4, dtype, dev())
+    _build_into(full, f1, f2)
+    part = sb.FusedPyramid(B, H, W1, W2, 4, dtype, dev())
+    part.buffer.fill_(12345.0)
+    _build_into(part, f1, f2, _lib.BUILD_SKIP_ODD_LEVELS)
+    assert part.c.levels_missing == 0b1010
+    for i in (0, 2):
+        assert torch.equal(part._level_view(i), full._level_view(i))
+    for i in (1, 3):
+        assert bool((part._level_view(i) == 12345.0).all())          # never written
+    part.materialize()
+    assert part.c.levels_missing == 0
+    for i in range(4):
+        assert torch.equal(part.level(i), full.level(i))
+    # the blocks use the flag for radius-4 volumes beyond L2 (or when forced) and build everything otherwise
+    import smoe_stereo_b200.corr as corr_mod
+    assert sb.CorrBlock1D(f1, f2)._state.pyr.c.levels_missing == 0          # small volume: all levels
+    old = corr_mod._skip_odd_levels
+    try:
+        corr_mod._skip_odd_levels = True
+        assert sb.CorrBlock1D(f1, f2)._state.pyr.c.levels_missing == 0b1010
+        assert sb.CorrBlock1D(f1, f2, radius=3)._state.pyr.c.levels_missing == 0
+        assert sb.CorrBlock1D(f1, f2, num_levels=2)._state.pyr.c.levels_missing == 0b10
+    finally:
+        corr_mod._skip_odd_levels = old

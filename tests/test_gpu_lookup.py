@@ -148,8 +148,25 @@ def test_thread_per_pixel_kernel_equals_lane_group_kernels_bitwise(sb, dtype, le
         f1 = torch.randn(B, C, H, W1, generator=g).to(dev()).to(dtype)
         f2 = torch.randn(B, C, H, W2, generator=g).to(dev()).to(dtype)
         cls = sb.CorrBlock1D if dtype == torch.float32 else sb.CorrBlockFast1D
-        blk = cls(f1, f2, num_levels=levels)
+        import smoe_stereo_b200.corr as corr_mod
+        old_skip = corr_mod._skip_odd_levels
+        try:
+            corr_mod._skip_odd_levels = True      # as for volumes beyond L2: levels 1/3 are not written
+            blk = cls(f1, f2, num_levels=levels)
+        finally:
+            corr_mod._skip_odd_levels = old_skip
         coords = torch.from_numpy(make_coords(B, H, W1, W2, 3, seed=W1)).to(dev())
+        if levels > 1:
+            # the block's build skipped levels 1/3: the lane-group kernels must refuse such a pyramid
+            L.smoe_corr_debug_set_lookup_kernel(3)
+            try:
+                with pytest.raises(RuntimeError, match="were not built"):
+                    blk(coords[0])
+            finally:
+                L.smoe_corr_debug_set_lookup_kernel(-1)
+            px_first = blk(coords[0]).clone()        # px on the two-level pyramid ...
+            blk._state.pyr.materialize()             # ... == px / vec / pair on the completed one
+            assert torch.equal(blk(coords[0]), px_first)
         coords[0, 0, 0, 0, :6] = torch.tensor([float("nan"), float("inf"), -float("inf"), 3e9, -0.0, W2 - 1.0])
         coords[1, 0, 0, 1, :4] = torch.tensor([-4.0, -4.5, W2 + 3.999, W2 + 4.0])
         outs = {}
