@@ -346,8 +346,8 @@ def main():
         t = traffic.get(key) if args.workload == "cfg1" else None
         return (t["read"] + t["write"]) if t else None
 
-    roofline = roof(lookup_bytes, t_lookup, ncu_traffic("lookup_fwd_px_kernel<float,float,4,4,false,false>@cfg1"))
-    roofline["kernel"] = "lookup_fwd_px_kernel<float,float,4,4,false,false>"
+    roofline = roof(lookup_bytes, t_lookup, ncu_traffic("lookup_fwd_px_kernel<float,float,4,4,false,true>@cfg1"))
+    roofline["kernel"] = "lookup_fwd_px_kernel<float,float,4,4,false,true>"
     roofline["us_per_launch_standalone"] = t_lookup_alone * 1e6
     roofline["how"] = ("(event-timed step - event-timed build) / 32 lookups, i.e. the launches inside the timed "
                        "region; us_per_launch_standalone = lookups-only graphs over rotating (L2-cold) input sets")

@@ -953,10 +953,12 @@ static void launch_fwd_px(const PyrDev& d, const float* coords, long long cbs, f
                           int HW, int B, cudaStream_t st, const CoordUpd& upd) {
   constexpr int NP = (NL + 1) / 2;
   const bool big = volume_exceeds_l2(d, (long long)HW * B, (int)sizeof(VT));
-  // measured (tools/px_sweep.sh): 32 pixels per CTA everywhere; one thread per level pair for
-  // volumes beyond L2 (cfg2 10.2 -> 8.9 us, cfg3 fp16 18.6 -> 12.4 us) and for fp16 volumes
-  // (cfg1 3.40 -> 3.16 us), one thread per pixel for L2-resident fp32 volumes (cfg1 3.02 vs 3.08 us)
-  const bool split = NP > 1 && (g_px_split >= 0 ? g_px_split != 0 : (big || sizeof(VT) == 2));
+  // measured (tools/px_sweep.sh, bench.py): 32 pixels per CTA and one thread per level pair
+  // everywhere -- beyond L2 (cfg2 10.2 -> 8.9 us, cfg3 fp16 18.6 -> 12.4 us), for fp16 volumes
+  // (cfg1 3.40 -> 3.16 us) and, inside a real step (cold coordinates, distinct output buffers),
+  // for L2-resident fp32 volumes too: 3.38 -> 3.10 us per lookup of the cfg1 bench step, although
+  // a lookups-only graph with warm coordinates had shown 3.02 vs 3.08 us
+  const bool split = NP > 1 && (g_px_split >= 0 ? g_px_split != 0 : true);
   int tpb = (g_px_tpb == 32 || g_px_tpb == 64 || g_px_tpb == 128) ? g_px_tpb : 32;
   dim3 grid((HW + tpb - 1) / tpb, B);
   OT* o = static_cast<OT*>(out);

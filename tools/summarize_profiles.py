@@ -45,7 +45,7 @@ if __name__ == "__main__":
     t = {"_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures in this "
                   "directory (cold-cache, serialised replays); read by bench.py for roofline.traffic"}
     v = metrics("lookup_cfg1.ncu-rep", "ncu_lookup_cfg1.txt")
-    t["lookup_fwd_px_kernel<float,float,4,4,false,false>@cfg1"] = {
+    t["lookup_fwd_px_kernel<float,float,4,4,false,true>@cfg1"] = {
         "read": v["dram__bytes_read.sum"], "write": v["dram__bytes_write.sum"], "source": "ncu_lookup_cfg1.txt"}
     v = metrics("build_cfg1.ncu-rep", "ncu_build_cfg1.txt")
     t["corr_build_kernel<float,float>@cfg1"] = {
