@@ -76,3 +76,47 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.replace("no CPU", ""), f"{f} mentions the oracle"
+
+
+def _fake_pyramid(built, W2=240, levels=4, missing=0):
+    """A descriptor with plausible (never dereferenced) pointers: argument validation only."""
+    w, off, pitch = built.pyramid_layout(W2, levels, built.DTYPE_F32)
+    p = built.Pyramid()
+    for i in range(levels):
+        p.level_ptr[i] = 0x10000000 + off[i] * 4
+        p.width[i] = w[i]
+        p.pitch[i] = pitch
+    p.num_levels, p.dtype = levels, built.DTYPE_F32
+    p.B, p.H, p.W1 = 1, 2, 8
+    p.levels_missing = missing
+    return p
+
+
+def test_unbuilt_levels_and_layout_flags_are_validated_without_a_gpu(built):
+    """smoe_pyramid_t.levels_missing (SMOE_BUILD_SKIP_ODD_LEVELS): entry points that would read a
+    level that was not built refuse before anything is launched; so does a channels-last build
+    whose channel count cannot be a TMA stride."""
+    L = built.lib()
+    fake = ctypes.c_void_p(0x20000000)
+    # radius 3 goes through the generic kernel, which reads every level
+    p = _fake_pyramid(built, missing=0b1010)
+    rc = L.smoe_corr_lookup(ctypes.byref(p), fake, 16, 1.0, 3, fake, built.DTYPE_F32, None)
+    assert rc == built.ERR_INVALID_ARG and "were not built" in built.last_error()
+    # an even level can never be marked missing
+    p = _fake_pyramid(built, missing=0b0100)
+    rc = L.smoe_corr_lookup(ctypes.byref(p), fake, 16, 1.0, 4, fake, built.DTYPE_F32, None)
+    assert rc == built.ERR_INVALID_ARG and "even level" in built.last_error()
+    # forcing a lane-group kernel on such a pyramid is refused as well
+    p = _fake_pyramid(built, missing=0b1010)
+    L.smoe_corr_debug_set_lookup_kernel(3)
+    try:
+        rc = L.smoe_corr_lookup(ctypes.byref(p), fake, 16, 1.0, 4, fake, built.DTYPE_F32, None)
+    finally:
+        L.smoe_corr_debug_set_lookup_kernel(-1)
+    assert rc == built.ERR_INVALID_ARG and "were not built" in built.last_error()
+    # channels-last needs C*sizeof(T) % 16 == 0
+    p = _fake_pyramid(built, W2=40)
+    p.H, p.W1 = 3, 40
+    rc = L.smoe_corr_build(fake, fake, built.DTYPE_F32, 1, 6, 3, 40, 40, ctypes.byref(p), 2.449,
+                           None, 0, built.BUILD_CHANNELS_LAST, None)
+    assert rc == built.ERR_UNSUPPORTED and "channels-last" in built.last_error()
