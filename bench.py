@@ -365,6 +365,7 @@ def main():
                                   "does not write levels 1 and 3 (the lookup recomputes them bit-exactly), so by "
                                   "design it moves %.1f MB" % (L, moved / 1e6))
         roofline_build["bytes_moved_by_design"] = moved
+        roofline_build["frac_on_bytes_moved"] = moved / t_build / 1e9 / hbm_peak
     roofline_build["tensor_tflops"] = build_flops / t_build / 1e12
     roofline_build["tensor_frac_of_tf32_peak"] = build_flops / t_build / 1e12 / tf_peak
 

@@ -44,9 +44,9 @@ _default_volume_dtype = torch.float16 if os.environ.get("SMOE_CORR_VOLUME_DTYPE"
 
 
 # SMOE_CORR_ALL_LEVELS=1: always write all four pyramid levels; =0: never write levels 1 and 3 for
-# radius-4 blocks; default: skip them only for volumes beyond L2 (see _CorrBlockBase.__init__)
+# radius-4 blocks (the default, see _CorrBlockBase.__init__)
 _skip_odd_levels = {"": None, "0": True, "1": False}.get(os.environ.get("SMOE_CORR_ALL_LEVELS", ""), None)
-_SKIP_ODD_MIN_BYTES = 96 << 20      # None above: skip levels 1/3 only for volumes beyond L2
+_SKIP_ODD_MIN_BYTES = 0             # None above: skip levels 1/3 for volumes of at least this size
 
 
 def set_default_volume_dtype(dtype) -> None:
@@ -433,11 +433,11 @@ class _CorrBlockBase:
             pyr_dtype = _default_volume_dtype
         st.num_levels, st.radius, st.pyr_dtype = num_levels, radius, pyr_dtype
         # The radius-4 lookup kernels read levels 0 and 2 only and recompute 1 and 3 (bit-exactly),
-        # so for volumes that stream through DRAM the build does not write them (a third of the
-        # pyramid bytes: cfg3 build 208 -> 191 us).  `corr_pyramid` and the cross-check kernels
-        # materialise them on demand (FusedPyramid.materialize).  L2-resident volumes keep all
-        # levels: there the shorter build was offset by slower first lookups (149 vs 145 us per
-        # cfg1 step, tools/step_probe.py).
+        # so the build does not write them (a third of the pyramid bytes: cfg1 build 29.6 -> 25.6 us,
+        # cfg3 208 -> 190 us).  `corr_pyramid` and the cross-check kernels materialise them on
+        # demand (FusedPyramid.materialize).  (With the one-thread-per-pixel lookup mapping the
+        # shorter build was offset by slower lookups at cfg1 -- 141.1 vs 138.5 us per step; with
+        # the per-level-pair mapping that is now the default it is a net gain, 127.1 vs 129.0 us.)
         st.build_flags = 0
         if radius == 4 and _skip_odd_levels is not False:
             vol_bytes = (fmap1.shape[0] * fmap1.shape[2] * fmap1.shape[3] * fmap2.shape[3] * 15 // 8

@@ -314,11 +314,14 @@ def test_build_skip_odd_levels_equals_full_build(sb, shape, dtype):
     assert part.c.levels_missing == 0
     for i in range(4):
         assert torch.equal(part.level(i), full.level(i))
-    # the blocks use the flag for radius-4 volumes beyond L2 (or when forced) and build everything otherwise
+    # the blocks use the flag for radius 4 (unless SMOE_CORR_ALL_LEVELS=1) and build everything otherwise
     import smoe_stereo_b200.corr as corr_mod
-    assert sb.CorrBlock1D(f1, f2)._state.pyr.c.levels_missing == 0          # small volume: all levels
+    if corr_mod._skip_odd_levels is None:
+        assert sb.CorrBlock1D(f1, f2)._state.pyr.c.levels_missing == 0b1010
     old = corr_mod._skip_odd_levels
     try:
+        corr_mod._skip_odd_levels = False
+        assert sb.CorrBlock1D(f1, f2)._state.pyr.c.levels_missing == 0
         corr_mod._skip_odd_levels = True
         assert sb.CorrBlock1D(f1, f2)._state.pyr.c.levels_missing == 0b1010
         assert sb.CorrBlock1D(f1, f2, radius=3)._state.pyr.c.levels_missing == 0
