@@ -246,7 +246,8 @@ void smoe_corr_debug_set_timeline(void* device_buffer);
 /*
  * Debug aid: force one forward lookup kernel on the calling thread (parity tests compare the
  * kernels bit for bit).  0 = automatic choice by volume size, 1 = thread-per-pixel kernel,
- * 2 = level-pair lane-group kernel, 3 = four-window lane-group kernel, -1 = back to the
+ * 2 = level-pair lane-group kernel, 3 = four-window lane-group kernel, 4 = thread-per-pixel kernel
+ * with 256-bit loads (fp32 volumes; experimental), -1 = back to the
  * SMOE_CORR_LOOKUP_KERNEL environment setting.  Shapes a kernel does not cover fall through to
  * the automatic choice.
  */

@@ -20,6 +20,8 @@
 //  * generic scalar kernels cover unaligned widths / pitches and radii other than 4.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "px_gather.cuh"
 
@@ -271,11 +273,13 @@ lookup_fwd_pair_kernel(PyrDev pyr, const float* __restrict__ coords, long long c
 // SPLIT: blockDim.y = number of level pairs and each thread handles ONE pair of its pixel (half
 // the dependent instruction chain and registers per thread, twice the threads): for L2-resident
 // volumes, where the kernel is bound by the latency of that chain rather than by throughput.
-template <typename VT, typename OT, int R, int NL, bool STREAM, bool SPLIT>
+// LD256: fp32 volumes fetched with 256-bit loads (PxPair256; opt-in, SMOE_CORR_PX_LD256=1).
+template <typename VT, typename OT, int R, int NL, bool STREAM, bool SPLIT, bool LD256 = false>
 __global__ void __launch_bounds__(256)
 lookup_fwd_px_kernel(PyrDev pyr, const float* __restrict__ coords, long long coords_bstride,
                      float coord_scale, OT* __restrict__ out, int HW, CoordUpd upd) {
-  using Pair = PxPair<VT, STREAM>;
+  static_assert(!LD256 || sizeof(VT) == 4, "256-bit segment loads are implemented for fp32 volumes");
+  using Pair = typename std::conditional<LD256, PxPair256<STREAM>, PxPair<VT, STREAM>>::type;
   constexpr int RD = 2 * R + 1;
   constexpr int NP = (NL + 1) / 2;
   constexpr int NPT = SPLIT ? 1 : NP;                         // pairs per thread
@@ -297,7 +301,8 @@ lookup_fwd_px_kernel(PyrDev pyr, const float* __restrict__ coords, long long coo
     const bool first = pr == 0 || NP == 1;
     const VT* fine_row = static_cast<const VT*>(first ? pyr.ptr[0] : pyr.ptr[2]) +
                          row * (first ? pyr.pitch[0] : pyr.pitch[2]);
-    pair[i].load(fine_row, first ? pyr.width[0] : pyr.width[2], x0 * (pr == 0 ? 1.0f : 0.25f));
+    pair[i].load(reinterpret_cast<const typename std::conditional<LD256, float, VT>::type*>(fine_row),
+                 first ? pyr.width[0] : pyr.width[2], x0 * (pr == 0 ? 1.0f : 0.25f));
   }
   pdl_launch_dependents();
 
@@ -962,6 +967,23 @@ static void launch_fwd_px(const PyrDev& d, const float* coords, long long cbs, f
   int tpb = (g_px_tpb == 32 || g_px_tpb == 64 || g_px_tpb == 128) ? g_px_tpb : 32;
   dim3 grid((HW + tpb - 1) / tpb, B);
   OT* o = static_cast<OT*>(out);
+  if constexpr (sizeof(VT) == 4 && sizeof(OT) == 4) {
+    // 256-bit segment loads for fp32 volumes that stream from DRAM (tools/px256_check.py, 32 distinct
+    // outputs per graph: cfg2 12.3 -> 8.4 us, cfg3 24.2 -> 20.5 us; L2-resident cfg1 3.08 -> 3.15 us,
+    // so those keep the 16-byte loads).  SMOE_CORR_PX_LD256=1 / 0 forces them on / off.  Level-0 rows
+    // must be 32-byte aligned (the first chunk of a level may start 16 bytes before it, which is
+    // only inside the pixel row for levels > 0).
+    static const int env256 = [] { const char* e = getenv("SMOE_CORR_PX_LD256"); return e ? (e[0] != '0' ? 1 : 0) : -1; }();
+    const bool ok256 = (reinterpret_cast<uintptr_t>(d.ptr[0]) & 31) == 0 && (d.pitch[0] * 4) % 32 == 0;
+    const bool want256 = g_fwd_kernel == 4 || (g_fwd_kernel == 0 && (env256 >= 0 ? env256 == 1 : big));
+    if (want256 && ok256) {
+      constexpr bool kSplit = NP > 1;
+      dim3 block(tpb, kSplit ? NP : 1);
+      if (big) launch_kernel_pdl(lookup_fwd_px_kernel<VT, OT, 4, NL, true, kSplit, true>, grid, block, 0, st, d, coords, cbs, cs, o, HW, upd);
+      else launch_kernel_pdl(lookup_fwd_px_kernel<VT, OT, 4, NL, false, kSplit, true>, grid, block, 0, st, d, coords, cbs, cs, o, HW, upd);
+      return;
+    }
+  }
   if (split) {
     constexpr int NLS = NP > 1 ? NL : 4;      // (never launched for NP == 1; avoids instantiating it)
     dim3 block(tpb, NP);
@@ -980,7 +1002,7 @@ static void dispatch_fwd_vec(int NL, const PyrDev& d, const float* coords, long 
   // Default: the thread-per-pixel kernel (faster than both lane-group kernels at every size and
   // dtype measured, tools/lookup_kernels_probe.py).  The lane-group kernels stay selectable
   // (smoe_corr_debug_set_lookup_kernel / SMOE_CORR_LOOKUP_KERNEL) as bit-exact cross-checks.
-  if (g_fwd_kernel == 0 || g_fwd_kernel == 1) {
+  if (g_fwd_kernel == 0 || g_fwd_kernel == 1 || g_fwd_kernel == 4) {
     switch (NL) {
       case 1: launch_fwd_px<VT, OT, 1>(d, coords, cbs, cs, out, HW, B, st, upd); break;
       case 2: launch_fwd_px<VT, OT, 2>(d, coords, cbs, cs, out, HW, B, st, upd); break;
@@ -1071,7 +1093,7 @@ static int lookup_impl(const smoe_pyramid_t* pyr, const float* coords, int64_t c
     // which reads levels 0 and 2 and recomputes 1 and 3, can serve the lookup
     SMOE_REQUIRE((pyr->levels_missing & 0x5) == 0, SMOE_ERR_INVALID_ARG,
                  "lookup: an even level is marked missing (levels_missing=0x%x)", pyr->levels_missing);
-    SMOE_REQUIRE(radius == 4 && pyramid_vec_ok(pyr) && (g_fwd_kernel == 0 || g_fwd_kernel == 1),
+    SMOE_REQUIRE(radius == 4 && pyramid_vec_ok(pyr) && (g_fwd_kernel == 0 || g_fwd_kernel == 1 || g_fwd_kernel == 4),
                  SMOE_ERR_INVALID_ARG,
                  "lookup: levels 0x%x of the pyramid were not built; radius %d / this kernel choice "
                  "needs them (build without SMOE_BUILD_SKIP_ODD_LEVELS)", pyr->levels_missing, radius);

@@ -103,4 +103,87 @@ struct PxPair {
   }
 };
 
+// fp32 volumes, 256-bit loads (LDG.E.256, sm_100): the segment is fetched as up to four 32-byte
+// chunks aligned to 32 bytes in MEMORY (level starts are only 16-byte aligned, so the first chunk
+// may begin 4 floats before the level: those elements are masked).  3.25 load instructions per
+// segment on average instead of 5.5 -- a third fewer L1 wavefronts, the busiest unit of the
+// streaming lookup (profiles/r01/README.md) -- for 12 more registers per pair.
+template <bool STREAM>
+struct PxPair256 {
+  static constexpr int R = 4, RD = 2 * R + 1;
+  static constexpr int SEG = 4 * R + 4;
+  static constexpr int NCH = 4, NV = 32;
+
+  float v[NV];
+  float dxf, dxc;
+  int sh;       // where the segment starts inside the first 32-byte chunk: 0, 2, 4 or 6 floats
+  int odd;      // basef - S - R: 0 or 1 (-1: parked coordinate, everything is zero)
+  int i0;       // fine index of v[0] (may be negative)
+
+  __device__ __forceinline__ static void load32(const float* p, float (&t)[8]) {
+    if (STREAM)
+      asm volatile("ld.global.L1::no_allocate.L2::64B.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                   : "=f"(t[0]), "=f"(t[1]), "=f"(t[2]), "=f"(t[3]), "=f"(t[4]), "=f"(t[5]), "=f"(t[6]), "=f"(t[7])
+                   : "l"(p));
+    else
+      asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                   : "=f"(t[0]), "=f"(t[1]), "=f"(t[2]), "=f"(t[3]), "=f"(t[4]), "=f"(t[5]), "=f"(t[6]), "=f"(t[7])
+                   : "l"(p));
+  }
+
+  __device__ __forceinline__ void load(const float* __restrict__ fine_row, int width, float xl) {
+    int basef, basec;
+    split_coord(xl, R, basef, dxf);
+    split_coord(xl * 0.5f, R, basec, dxc);
+    const int S = 2 * basec;
+    const int o = basef - S - R;
+    odd = (o == 0 || o == 1) ? o : -1;
+    const int m = (int)((reinterpret_cast<uintptr_t>(fine_row) >> 2) & 7);   // 0 or 4 (16-byte aligned rows)
+    const int c8 = (S + m) >> 3;                      // arithmetic shift == floor division
+    sh = (S + m) - (c8 << 3);
+    i0 = (c8 << 3) - m;
+    const float* src = fine_row + i0;                 // 32-byte aligned
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      const int ij = i0 + 8 * j;
+      float t[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) t[e] = 0.f;
+      // the last chunk is only needed when the segment starts 6 floats into the first one
+      const bool need = odd >= 0 && (j < NCH - 1 || sh + SEG > 8 * (NCH - 1)) && ij + 8 > 0 && ij < width;
+      if (need) load32(src + 8 * j, t);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[8 * j + e] = t[e];
+    }
+    if (__builtin_expect(i0 < 0 || i0 + NV > width, 0)) {      // rare: the chunks reach outside [0, width)
+#pragma unroll
+      for (int k = 0; k < NV; ++k)
+        if ((unsigned)(i0 + k) >= (unsigned)width) v[k] = 0.f;
+    }
+  }
+
+  template <typename LT>
+  __device__ __forceinline__ void coarse(int wc, float (&out)[RD]) const {
+    float pc[NV / 2];
+#pragma unroll
+    for (int j = 0; j < NV / 2; ++j) pc[j] = (v[2 * j] + v[2 * j + 1]) * 0.5f;
+    const int c0 = i0 >> 1;                           // coarse column of pc[0] (i0 is even)
+    if (__builtin_expect(c0 < 0 || c0 + NV / 2 > wc, 0)) {
+#pragma unroll
+      for (int j = 0; j < NV / 2; ++j)
+        if ((unsigned)(c0 + j) >= (unsigned)wc) pc[j] = 0.f;
+    }
+    shift_down<NV / 2, 2>(pc, sh >> 1);
+#pragma unroll
+    for (int k = 0; k < RD; ++k) out[k] = to_float(lerp_ref<LT>(pc[k], pc[k + 1], dxc));
+  }
+
+  template <typename LT>
+  __device__ __forceinline__ void fine(float (&out)[RD]) {
+    shift_down<NV, 3>(v, sh + (odd > 0 ? 1 : 0));
+#pragma unroll
+    for (int k = 0; k < RD; ++k) out[k] = to_float(lerp_ref<LT>(v[R + k], v[R + k + 1], dxf));
+  }
+};
+
 }  // namespace smoe

@@ -171,7 +171,7 @@ def test_thread_per_pixel_kernel_equals_lane_group_kernels_bitwise(sb, dtype, le
         coords[1, 0, 0, 1, :4] = torch.tensor([-4.0, -4.5, W2 + 3.999, W2 + 4.0])
         outs = {}
         try:
-            for which, name in ((1, "px"), (2, "pair"), (3, "vec")):
+            for which, name in ((1, "px"), (2, "pair"), (3, "vec"), (4, "px256")):
                 L.smoe_corr_debug_set_lookup_kernel(which)
                 outs[name] = [blk(coords[t]).clone() for t in range(3)]
         finally:
@@ -179,6 +179,7 @@ def test_thread_per_pixel_kernel_equals_lane_group_kernels_bitwise(sb, dtype, le
         for t in range(3):
             assert torch.equal(outs["px"][t], outs["vec"][t]), (B, C, H, W1, W2, t)
             assert torch.equal(outs["pair"][t], outs["vec"][t])     # (pair falls through to vec for 1/3 levels)
+            assert torch.equal(outs["px256"][t], outs["vec"][t])    # 256-bit loads (fp32 volumes; else == px)
             assert torch.isfinite(outs["px"][t]).all()
 
 
