@@ -47,7 +47,7 @@
 extern "C" {
 #endif
 
-#define SMOE_CORR_ABI_VERSION 1
+#define SMOE_CORR_ABI_VERSION 2
 #define SMOE_MAX_LEVELS 4
 
 /* error codes */
@@ -210,8 +210,9 @@ int smoe_corr_lookup_bwd(const smoe_pyramid_t* grad_pyr, const float* coords,
  * gradient pyramid, a memset and a fold pass.  g0 describes that level-0 output (fp32; level_ptr[0],
  * width[0] = W2, pitch[0]); accumulate != 0 adds to its current contents.  Result ==
  * smoe_corr_lookup_bwd(ACCUMULATE) x num_iters followed by smoe_corr_fold_pyramid_grad.
- * Host arrays of num_iters device pointers / strides.  Radius 4, H*W1*sizeof(grad) % 16 == 0 and
- * 16-byte-aligned operands required (SMOE_ERR_UNSUPPORTED otherwise: use the per-call path).
+ * Host arrays of num_iters device pointers / strides.  Radius 4 only, and W2 small enough for the
+ * gradient rows of 32 pixels to fit shared memory (W2 <= ~900 for 4 levels); SMOE_ERR_UNSUPPORTED
+ * otherwise: use the per-call path.  No alignment rule on the gradient planes or coordinates.
  */
 int smoe_corr_lookup_bwd_batched(const smoe_pyramid_t* g0, int num_levels, int num_iters,
                                  const float* const* coords, const int64_t* coords_batch_stride,
@@ -225,33 +226,29 @@ int smoe_corr_lookup_bwd_batched(const smoe_pyramid_t* g0, int num_levels, int n
 int smoe_corr_fold_pyramid_grad(const smoe_pyramid_t* grad_pyr, smoe_stream_t stream);
 
 /*
+ * Fill in the levels a build with SMOE_BUILD_SKIP_ODD_LEVELS left unwritten: for every bit i set in
+ * pyr->levels_missing (i >= 1, level i-1 present or filled earlier in the same call)
+ *   level i[., j] = (level i-1[., 2j] + level i-1[., 2j+1]) * 0.5      (fp32 sum, one rounding)
+ * -- the arithmetic of the build epilogue / F.avg_pool2d (core/corr.py:124), so the result is
+ * bit-identical to a full build.  Only consumers other than the radius-4 lookup need it (the
+ * reference-shaped `corr_pyramid` views, core/corr.py:41).  The caller clears levels_missing.
+ */
+int smoe_corr_fill_levels(const smoe_pyramid_t* pyr, smoe_stream_t stream);
+
+/*
  * Volume-build backward on tcgen05 tensor cores (kind::tf32): with G = grad_pyr level 0 after
  * smoe_corr_fold_pyramid_grad (fp32),
  *   dfmap1[b,c,h,w1] = (sum_w2 G[(b,h,w1),w2] * fmap2[b,c,h,w2]) / denom
  *   dfmap2[b,c,h,w2] = (sum_w1 G[(b,h,w1),w2] * fmap1[b,c,h,w1]) / denom
  * i.e. the autograd of core/corr.py:154-156 (einsum, then / sqrt(D)).  fp32 NCHW feature maps and
- * outputs; W1 and W2 must be multiples of 4 (TMA 16-byte strides) -- SMOE_ERR_UNSUPPORTED otherwise.
+ * outputs.  row_pitch1 / row_pitch2 = elements between consecutive image rows of fmap1+dfmap1 /
+ * fmap2+dfmap2 (>= W, a multiple of 4: TMA wants 16-byte strides; pass W itself for contiguous
+ * tensors whose W is a multiple of 4, a padded pitch otherwise).  Strides: (C*H*pitch, H*pitch, pitch, 1).
  */
 int smoe_corr_build_bwd(const void* fmap1, const void* fmap2, int in_dtype, int B, int C, int H,
-                        int W1, int W2, const smoe_pyramid_t* grad_pyr, float denom, void* dfmap1,
-                        void* dfmap2, smoe_stream_t stream);
-
-/*
- * Debug aid (not part of the reference interface): when a device buffer of
- * 148 * 3 * 16 int64 is set on the calling thread, the next smoe_corr_build launches record
- * per-CTA clock64 stamps of the producer / MMA / epilogue roles into it.  NULL disables.
- */
-void smoe_corr_debug_set_timeline(void* device_buffer);
-
-/*
- * Debug aid: force one forward lookup kernel on the calling thread (parity tests compare the
- * kernels bit for bit).  0 = automatic choice by volume size, 1 = thread-per-pixel kernel,
- * 2 = level-pair lane-group kernel, 3 = four-window lane-group kernel, 4 = thread-per-pixel kernel
- * with 256-bit loads (fp32 volumes; experimental), -1 = back to the
- * SMOE_CORR_LOOKUP_KERNEL environment setting.  Shapes a kernel does not cover fall through to
- * the automatic choice.
- */
-void smoe_corr_debug_set_lookup_kernel(int which);
+                        int W1, int W2, int64_t row_pitch1, int64_t row_pitch2,
+                        const smoe_pyramid_t* grad_pyr, float denom, void* dfmap1, void* dfmap2,
+                        smoe_stream_t stream);
 
 #ifdef __cplusplus
 }

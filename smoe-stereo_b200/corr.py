@@ -123,6 +123,9 @@ class FusedPyramid:
         self.c.B, self.c.H, self.c.W1 = B, H, W1
         self.c.levels_missing = 0
         self.ref = ctypes.byref(self.c)
+        self.addr = ctypes.addressof(self.c)
+        self.out_ring = None                            # [buffers, next]: see _CorrBlockBase.reuse_outputs
+        self.ring_radius = 0
         # cached for the eager per-call path (_lookup): device ordinal, coords plane geometry
         self.dev_idx = device.index if device.index is not None else _raw_device()
         self._coords_fast = (H * W1, W1, 1)          # strides (ch, H, W) of a contiguous coords tensor
@@ -142,19 +145,16 @@ class FusedPyramid:
         self.c.levels_missing = mask & ((1 << self.num_levels) - 1)
 
     def materialize(self) -> None:
-        """Fill in the levels the build skipped: level i = pair average of level i-1, with the very
-        arithmetic of the build epilogue / F.avg_pool2d (fp32 sum, * 0.5, one rounding), so the
-        result is bit-identical to a build without SMOE_BUILD_SKIP_ODD_LEVELS.  Only needed by
-        consumers other than the radius-4 lookup kernels (`corr_pyramid`, cross-check kernels)."""
-        missing = self.c.levels_missing
-        for i in range(1, self.num_levels):
-            if (missing >> i) & 1:
-                w = self.widths[i]
-                prev = self._level_view(i - 1)
-                if w > 0:
-                    avg = (prev[..., 0:2 * w:2].float() + prev[..., 1:2 * w:2].float()) * 0.5
-                    self._level_view(i).copy_(avg.to(self.dtype))
-        self.c.levels_missing = 0
+        """Fill in the levels the build skipped (smoe_corr_fill_levels): level i = pair average of
+        level i-1 with the very arithmetic of the build epilogue / F.avg_pool2d (fp32 sum, * 0.5,
+        one rounding), so the result is bit-identical to a build without
+        SMOE_BUILD_SKIP_ODD_LEVELS.  Only needed by consumers other than the radius-4 lookup
+        kernels (`corr_pyramid`)."""
+        if self.c.levels_missing:
+            with _on_device(self.device):
+                rc = _lib.lib().smoe_corr_fill_levels(self.ref, _stream_ptr(self.device))
+            _lib.check(rc, "smoe_corr_fill_levels")
+            self.c.levels_missing = 0
 
 
 def _is_channels_last(t: torch.Tensor) -> bool:
@@ -177,7 +177,12 @@ def _layout_for_build(fmap1: torch.Tensor, fmap2: torch.Tensor):
         f2 = fmap2.contiguous(memory_format=torch.channels_last)
         if f1.data_ptr() % 16 == 0 and f2.data_ptr() % 16 == 0:
             return f1, f2
-    return fmap1.contiguous(), fmap2.contiguous()
+    return _aligned16(fmap1.contiguous()), _aligned16(fmap2.contiguous())
+
+
+def _aligned16(t: torch.Tensor) -> torch.Tensor:
+    """TMA wants 16-byte-aligned bases; a contiguous view that starts mid-allocation is cloned."""
+    return t if t.data_ptr() % 16 == 0 else t.clone(memory_format=torch.contiguous_format)
 
 
 def _build_into(pyr: FusedPyramid, fmap1: torch.Tensor, fmap2: torch.Tensor, flags: int = 0) -> None:
@@ -204,29 +209,40 @@ def _build_into(pyr: FusedPyramid, fmap1: torch.Tensor, fmap2: torch.Tensor, fla
         ws.record_stream(torch.cuda.current_stream(fmap1.device))
 
 
+def _pitched_f32(t: torch.Tensor):
+    """(tensor whose image rows are `pitch` elements apart with pitch % 4 == 0, pitch, is_copy):
+    the operand layout smoe_corr_build_bwd reads/writes by TMA (16-byte strides)."""
+    W = t.shape[3]
+    t = t.float()
+    if W % 4 == 0:
+        return _aligned16(t.contiguous()), W, False
+    Wp = (W + 3) // 4 * 4
+    buf = t.new_zeros(t.shape[:3] + (Wp,))
+    buf[..., :W].copy_(t)
+    return buf, Wp, True
+
+
 def _build_backward(gp: FusedPyramid, fmap1: torch.Tensor, fmap2: torch.Tensor):
     """Autograd of core/corr.py:154-156 given the folded level-0 gradient in `gp`:
     d fmap1 = G . fmap2^T / sqrt(C), d fmap2 = G^T . fmap1^T / sqrt(C)  (smoe_corr_build_bwd,
-    tcgen05 kind::tf32).  W not a multiple of 4 violates TMA's 16-byte stride rule for the NCHW
-    operands; those shapes (never produced by the model: images are padded to /32,
-    dataloader/utils.py:260-267) take the cuBLAS einsum instead."""
+    tcgen05 kind::tf32).  Widths that are not multiples of 4 (never produced by the model: images
+    are padded to /32, dataloader/utils.py:260-267) violate TMA's 16-byte stride rule for NCHW
+    operands; they run the same kernel on pitch-padded copies."""
     B, C, H, W1 = fmap1.shape
     W2 = fmap2.shape[3]
-    f1 = fmap1.float().contiguous()
-    f2 = fmap2.float().contiguous()
-    if W1 % 4 == 0 and W2 % 4 == 0 and f1.data_ptr() % 16 == 0 and f2.data_ptr() % 16 == 0:
-        df1 = torch.empty_like(f1)
-        df2 = torch.empty_like(f2)
-        with _on_device(gp.device):
-            rc = _lib.lib().smoe_corr_build_bwd(f1.data_ptr(), f2.data_ptr(), _lib.DTYPE_F32, B, C, H, W1,
-                                                W2, gp.ref, math.sqrt(C), df1.data_ptr(), df2.data_ptr(),
-                                                _stream_ptr(gp.device))
-        _lib.check(rc, "smoe_corr_build_bwd")
-    else:
-        g0 = gp.level(0)                                    # (B,H,W1,W2) fp32, strided view
-        scale = 1.0 / math.sqrt(C)
-        df1 = torch.einsum("bhkw,bchw->bchk", g0, f2).mul_(scale)
-        df2 = torch.einsum("bhkw,bchk->bchw", g0, f1).mul_(scale)
+    f1, p1, _ = _pitched_f32(fmap1)
+    f2, p2, _ = _pitched_f32(fmap2)
+    df1 = torch.empty((B, C, H, p1), dtype=torch.float32, device=f1.device)
+    df2 = torch.empty((B, C, H, p2), dtype=torch.float32, device=f2.device)
+    with _on_device(gp.device):
+        rc = _lib.lib().smoe_corr_build_bwd(f1.data_ptr(), f2.data_ptr(), _lib.DTYPE_F32, B, C, H, W1, W2,
+                                            p1, p2, gp.ref, math.sqrt(C), df1.data_ptr(), df2.data_ptr(),
+                                            _stream_ptr(gp.device))
+    _lib.check(rc, "smoe_corr_build_bwd")
+    if p1 != W1:
+        df1 = df1[..., :W1].contiguous()
+    if p2 != W2:
+        df2 = df2[..., :W2].contiguous()
     return df1.to(fmap1.dtype), df2.to(fmap2.dtype)
 
 
@@ -289,59 +305,102 @@ def _coords_plane(coords: torch.Tensor, B: int, H: int, W1: int):
     if coords.dtype != torch.float32:
         coords = coords.float()
     st = coords.stride()
-    if st[3] != 1 or st[2] != W1:
+    if st[3] != 1 or st[2] != W1 or (B > 1 and st[0] < H * W1):      # strided, or a broadcast batch
         coords = coords[:, :1].contiguous()
         st = coords.stride()
     return coords, (st[0] if B > 1 else max(st[0], H * W1))
 
 
 _lookup_fn = None
+_warned_coords_grad = False
 
 
-def _lookup(pyr: FusedPyramid, coords: torch.Tensor, radius: int, out_dtype) -> torch.Tensor:
-    """One eager lookup.  This is the call an unmodified model makes once per GRU iteration, so the
-    host side is kept short (tools/eager_overhead.py): a contiguous fp32 CUDA coords tensor of the
-    right shape skips the general validation, the device switch and the stream wrapper objects."""
+def _warn_coords_grad() -> None:
+    """The reference's CorrBlock1D / PytorchAlternateCorrBlock1D sample with grid_sample and are
+    therefore differentiable w.r.t. coords; the models never use that (coords1 is detached right
+    before every lookup, core/SMoEStereo.py:234, core/raft_stereo.py:206) and neither does
+    corr_sampler (core/corr.py:29 returns None).  Here coords never receive a gradient."""
+    global _warned_coords_grad
+    if not _warned_coords_grad:
+        _warned_coords_grad = True
+        import warnings
+        warnings.warn("smoe_stereo_b200: coords.requires_grad is set, but the correlation lookup does not "
+                      "propagate gradients to coords (as corr_sampler, core/corr.py:29); detach them like "
+                      "core/SMoEStereo.py:234 does", RuntimeWarning, stacklevel=3)
+
+
+def _lookup(pyr: FusedPyramid, coords: torch.Tensor, radius: int, out_dtype, use_ring: bool = False) -> torch.Tensor:
+    """One eager lookup.  This is the call an unmodified model makes once per GRU iteration, and its
+    kernel runs ~3 us, so the host side is kept short (tools/eager_overhead.py): a contiguous fp32
+    CUDA coords tensor of the right shape skips the general validation, the device switch and the
+    stream wrapper objects, and the C entry point is reached through the CPython binding
+    (_lib.fast_lookup) instead of ctypes."""
     global _lookup_fn
     if _lookup_fn is None:
-        _lookup_fn = _lib.lib().smoe_corr_lookup
+        _lookup_fn = _lib.fast_lookup()
     shp = coords.shape
     if (coords.dtype is torch.float32 and coords.is_cuda and len(shp) == 4 and shp[0] == pyr.B
-            and shp[2] == pyr.H and shp[3] == pyr.W1 and coords.stride()[1:] == pyr._coords_fast):
-        bstride = coords.stride(0) if pyr.B > 1 else shp[1] * pyr.H * pyr.W1
+            and shp[2] == pyr.H and shp[3] == pyr.W1 and coords.stride()[1:] == pyr._coords_fast
+            and (pyr.B == 1 or coords.stride(0) >= pyr._coords_fast[0])):
+        bstride = coords.stride(0) if pyr.B > 1 else shp[1] * pyr._coords_fast[0]
     else:
         coords, bstride = _coords_plane(coords, pyr.B, pyr.H, pyr.W1)
-    out = torch.empty((pyr.B, pyr.num_levels * (2 * radius + 1), pyr.H, pyr.W1), dtype=out_dtype,
-                      device=pyr.device)
+    ring = pyr.out_ring if use_ring else None
+    if ring is not None and ring[0][0].dtype is out_dtype and radius == pyr.ring_radius:
+        bufs, pos = ring
+        out = bufs[pos]
+        ring[1] = pos + 1 if pos + 1 < len(bufs) else 0
+    else:
+        out = torch.empty((pyr.B, pyr.num_levels * (2 * radius + 1), pyr.H, pyr.W1), dtype=out_dtype,
+                          device=pyr.device)
     idx = pyr.dev_idx
     if _raw_stream is not None and _raw_device() == idx:
-        rc = _lookup_fn(pyr.ref, coords.data_ptr(), bstride, 1.0, radius, out.data_ptr(),
+        rc = _lookup_fn(pyr.addr, coords.data_ptr(), bstride, radius, out.data_ptr(),
                         _DTYPE_CODE[out_dtype], _raw_stream(idx))
     else:
         with _on_device(pyr.device):
-            rc = _lookup_fn(pyr.ref, coords.data_ptr(), bstride, 1.0, radius, out.data_ptr(),
-                            _DTYPE_CODE[out_dtype], _stream_ptr(pyr.device))
+            rc = _lookup_fn(pyr.addr, coords.data_ptr(), bstride, radius, out.data_ptr(),
+                            _DTYPE_CODE[out_dtype], _stream_ptr(pyr.device).value or 0)
     if rc:
         _lib.check(rc, "smoe_corr_lookup")
     return out
 
 
 # ---------------------------------------------------------------------------- autograd plumbing
+# Deferred lookup backwards are flushed into the folded level-0 gradient every _FLUSH_EVERY items, so
+# at most that many (coords, grad_out) pairs -- B*36*H*W1 values each, 17 MB at cfg2 -- are kept
+# alive beyond the point where the reference would have freed them (it consumes each grad_out
+# inside its own sampler backward).  32 covers the reference's 16 / 22 / 32-iteration steps in ONE
+# launch (a flush re-reads and re-writes the level-0 gradient); longer loops stay bounded.
+_FLUSH_EVERY = 32
+
+
 class _State:
     """Per-block state shared by the build and lookup autograd nodes."""
 
     def __init__(self):
         self.pyr: FusedPyramid | None = None
-        self.grad_pyr: FusedPyramid | None = None      # per-call (accumulating) backward path
-        self.pending: list = []                        # deferred lookup backwards (batched path)
         self.radius = 4
         self.build_flags = 0
+        self.reset_backward()
+
+    def reset_backward(self):
+        """Forget everything a (possibly aborted) backward pass has accumulated."""
+        self.grad_pyr: FusedPyramid | None = None      # per-call (accumulating) backward path, all levels
+        self.g0: FusedPyramid | None = None            # folded level-0 gradient of flushed batches
+        self.pending: list = []                        # deferred lookup backwards (batched path)
+        self.seen: set = set()                         # lookup nodes that already ran in this pass
+
+    def flush_pending(self):
+        if self.pending:
+            self.g0 = _batched_lookup_backward(self.pyr, self.pending, self.radius, self.g0)
+            self.pending = []
 
 
 class _BuildFn(torch.autograd.Function):
     """Volume + pyramid build.  Returns a 1-element token; every lookup takes the token as an
     input, so autograd runs this node's backward ONCE, after all lookup backwards have
-    accumulated into state.grad_pyr."""
+    accumulated into the state."""
 
     @staticmethod
     def forward(ctx, fmap1, fmap2, state):
@@ -358,17 +417,22 @@ class _BuildFn(torch.autograd.Function):
     def backward(ctx, grad_token):
         fmap1, fmap2 = ctx.saved_tensors
         state = ctx.state
-        gp, pending = state.grad_pyr, state.pending
-        state.grad_pyr, state.pending = None, []
-        if gp is None and not pending:
-            return torch.zeros_like(fmap1), torch.zeros_like(fmap2), None
-        if gp is not None:          # lookups that went through the per-call accumulate path
-            with _on_device(gp.device):
-                rc = _lib.lib().smoe_corr_fold_pyramid_grad(gp.ref, _stream_ptr(gp.device))
-            _lib.check(rc, "smoe_corr_fold_pyramid_grad")
-        if pending:                 # all deferred lookups of the step in one pass (+ fold)
-            gp = _batched_lookup_backward(state.pyr, pending, state.radius, gp)
-        df1, df2 = _build_backward(gp, fmap1, fmap2)
+        try:
+            state.flush_pending()
+            gp, g0 = state.grad_pyr, state.g0
+            if gp is None and g0 is None:
+                return torch.zeros_like(fmap1), torch.zeros_like(fmap2), None
+            if gp is not None:          # lookups that went through the per-call accumulate path
+                with _on_device(gp.device):
+                    rc = _lib.lib().smoe_corr_fold_pyramid_grad(gp.ref, _stream_ptr(gp.device))
+                _lib.check(rc, "smoe_corr_fold_pyramid_grad")
+                if g0 is not None:      # a step that mixed both paths (different radii / dtypes)
+                    gp.level(0).add_(g0.level(0))
+            else:
+                gp = g0
+            df1, df2 = _build_backward(gp, fmap1, fmap2)
+        finally:
+            state.reset_backward()
         return df1, df2, None
 
 
@@ -385,9 +449,17 @@ class _LookupFn(torch.autograd.Function):
         (coords,) = ctx.saved_tensors
         state = ctx.state
         pyr = state.pyr
+        # A lookup node runs once per backward pass.  Seeing it again means the previous pass never
+        # reached the build node (an exception or OOM further down the graph, with retain_graph):
+        # what it left behind must not leak into this pass.
+        if id(ctx) in state.seen:
+            state.reset_backward()
+        state.seen.add(id(ctx))
         item = _batchable(pyr, coords, grad_out, state.radius)
         if item is not None:            # defer: the build backward handles the whole step at once
             state.pending.append(item)
+            if len(state.pending) >= _FLUSH_EVERY:
+                state.flush_pending()
             return torch.zeros(1, dtype=torch.float32, device=pyr.device), None, None, None
         if state.grad_pyr is None:      # zeroed once per backward pass, not once per call
             state.grad_pyr = FusedPyramid(pyr.B, pyr.H, pyr.W1, pyr.W2, pyr.num_levels,
@@ -462,9 +534,30 @@ class _CorrBlockBase:
     def __call__(self, coords):
         p = self._state.pyr
         out_dtype = torch.float32 if self._float_output else p.dtype
-        if self._token is not None and torch.is_grad_enabled():
-            return _LookupFn.apply(self._token, coords, self._state, out_dtype)
-        return _lookup(p, coords, self.radius, out_dtype)
+        if torch.is_grad_enabled():
+            if coords.requires_grad:
+                _warn_coords_grad()
+            if self._token is not None:
+                return _LookupFn.apply(self._token, coords, self._state, out_dtype)
+            return _lookup(p, coords, self.radius, out_dtype)
+        return _lookup(p, coords, self.radius, out_dtype, True)
+
+    def reuse_outputs(self, depth: int = 2):
+        """Opt-in: serve `__call__` from a ring of `depth` preallocated output buffers instead of a
+        fresh torch.empty per call (~3 us of host time per lookup, as long as the kernel itself at
+        B=1).  The result of a call is then only valid until `depth` further calls have been made --
+        fine for the GRU loop, which consumes corr inside the same iteration
+        (core/raft_stereo.py:207-214), not for callers that keep every lookup.  depth=0 restores
+        per-call allocation.  Ignored while autograd is recording."""
+        p = self._state.pyr
+        if depth <= 0:
+            p.out_ring = None
+            return self
+        dt = torch.float32 if self._float_output else p.dtype
+        p.out_ring = [[torch.empty((p.B, p.num_levels * (2 * self.radius + 1), p.H, p.W1), dtype=dt,
+                                   device=p.device) for _ in range(depth)], 0]
+        p.ring_radius = self.radius
+        return self
 
     def lookup_update(self, coords1, delta_flow=None, coords0=None):
         """Opt-in fused GRU-loop step.  Equivalent to the reference loop body
@@ -563,7 +656,7 @@ class _CorrBlockBase:
     @staticmethod
     def corr(fmap1, fmap2):
         """(B,D,H,W1),(B,D,H,W2) -> (B,H,W1,1,W2), same dtype (core/corr.py:148-156, :53-61).
-        Differentiable: backward is the einsum's (cuBLAS; see _BuildFn.backward)."""
+        Differentiable: backward = smoe_corr_build_bwd (see _build_backward)."""
         return _CorrVolumeFn.apply(fmap1, fmap2)
 
 
@@ -585,11 +678,9 @@ class _CorrVolumeFn(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, g):
         f1, f2 = ctx.saved_tensors
-        scale = 1.0 / math.sqrt(f1.shape[1])
-        g = g.squeeze(3).float()
-        df1 = torch.einsum("bhkw,bchw->bchk", g, f2.float()).mul_(scale).to(f1.dtype)
-        df2 = torch.einsum("bhkw,bchk->bchw", g, f1.float()).mul_(scale).to(f2.dtype)
-        return df1, df2
+        gp = FusedPyramid(f1.shape[0], f1.shape[2], f1.shape[3], f2.shape[3], 1, torch.float32, f1.device)
+        gp.level(0).copy_(g.squeeze(3))               # (B,H,W1,W2) -> pitched rows of the C ABI
+        return _build_backward(gp, f1, f2)
 
 
 class CorrBlock1D(_CorrBlockBase):

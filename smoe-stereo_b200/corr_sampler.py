@@ -32,12 +32,30 @@ def _check_input(x, name):
         raise RuntimeError(f"{name} must be contiguous")
 
 
+def _row_pitched(v: torch.Tensor) -> bool:
+    """(B,H,W1,W2) whose pixel rows are evenly `pitch` >= W2 elements apart -- what the
+    `corr_pyramid[i]` views of this package's own blocks are (one level of a fused pyramid row)."""
+    if v.dim() != 4 or v.stride(3) != 1:
+        return False
+    B, H, W1, W2 = v.shape
+    pitch = v.stride(2)
+    return pitch >= W2 and (H == 1 or v.stride(1) == W1 * pitch) and (B == 1 or v.stride(0) == H * W1 * pitch)
+
+
+def _check_volume(v):
+    """CHECK_INPUT(volume) of sampler/sampler.cpp:20-22, relaxed to admit row-pitched views."""
+    if not isinstance(v, torch.Tensor) or not v.is_cuda:
+        raise RuntimeError("volume must be a CUDA tensor")
+    if not (v.is_contiguous() or _row_pitched(v)):
+        raise RuntimeError("volume must be contiguous")
+
+
 def _planar(volume: torch.Tensor) -> _lib.Pyramid:
     B, H, W1, W2 = volume.shape
     p = _lib.Pyramid()
     p.level_ptr[0] = volume.data_ptr()
     p.width[0] = W2
-    p.pitch[0] = W2
+    p.pitch[0] = W2 if volume.is_contiguous() else volume.stride(2)
     p.num_levels = 1
     p.dtype = _DTYPE_CODE[volume.dtype]
     p.B, p.H, p.W1 = B, H, W1
@@ -65,7 +83,7 @@ def _launch_ctx(device):
 
 def forward(volume, coords, radius):
     """sampler_forward (sampler/sampler.cpp:24-32)."""
-    _check_input(volume, "volume")
+    _check_volume(volume)
     _check_input(coords, "coords")
     _check_shapes(volume, coords)
     B, H, W1, _ = volume.shape
@@ -83,7 +101,7 @@ def forward(volume, coords, radius):
 
 def backward(volume, coords, corr_grad, radius):
     """sampler_backward (sampler/sampler.cpp:34-45): fresh dense gradient w.r.t. volume."""
-    _check_input(volume, "volume")
+    _check_volume(volume)
     _check_input(coords, "coords")
     _check_input(corr_grad, "corr_grad")
     _check_shapes(volume, coords)
@@ -94,7 +112,7 @@ def backward(volume, coords, corr_grad, radius):
                            f"{tuple(corr_grad.shape)}")
     if corr_grad.dtype != volume.dtype:
         raise RuntimeError("corr_grad must have the volume's dtype")
-    grad = torch.empty_like(volume)
+    grad = torch.empty(volume.shape, dtype=volume.dtype, device=volume.device)
     p = _planar(grad)
     guard, stream = _launch_ctx(volume.device)
     with guard:

@@ -16,16 +16,44 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-// SMOE_CORR_PDL: unset -> 2 (programmatic dependent launch only for the kernels that measured
-// faster with it: the thread-per-pixel lookup), 0 -> never, anything else -> every kernel.
-int pdl_mode() {
-  static const int mode = [] {
-    const char* e = getenv("SMOE_CORR_PDL");
-    if (!e || !e[0]) return 2;
-    return e[0] == '0' ? 0 : 1;
-  }();
-  return mode;
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e && e[0]) ? atoi(e) : dflt;
 }
+
+static Tuning read_tuning() {
+  Tuning t;
+  // SMOE_CORR_PDL: unset -> 2 (only the kernels that measured faster with it), 0 -> never,
+  // anything else -> every kernel
+  if (const char* e = getenv("SMOE_CORR_PDL"))
+    if (e[0]) t.pdl = e[0] == '0' ? 0 : 1;
+#ifdef SMOE_CROSSCHECK
+  if (const char* e = getenv("SMOE_CORR_LOOKUP_KERNEL"))
+    t.fwd_kernel = e[0] == 'p' && e[1] == 'x' ? (e[2] == '2' ? 4 : 1) : (e[0] == 'p' ? 2 : (e[0] == 'v' ? 3 : 0));
+  t.px_tpb = env_int("SMOE_CORR_PX_TPB", t.px_tpb);
+  t.px_split = env_int("SMOE_CORR_PX_SPLIT", t.px_split);
+  t.px_ld256 = env_int("SMOE_CORR_PX_LD256", t.px_ld256);
+  t.px_hint = env_int("SMOE_CORR_PX_HINT", t.px_hint);
+  t.lookup_tile = env_int("SMOE_CORR_LOOKUP_TILE", t.lookup_tile);
+  if (const char* e = getenv("SMOE_CORR_BWD_BATCHED")) t.bwd_staged = e[0] == 's';
+  t.bwd_split = env_int("SMOE_CORR_BWD_SPLIT", t.bwd_split);
+  t.bwd_rowmod = env_int("SMOE_CORR_BWD_ROWMOD", t.bwd_rowmod);
+  t.build_pair = env_int("SMOE_CORR_BUILD_PAIR", 0);
+  t.build_stages = env_int("SMOE_CORR_BUILD_STAGES", 0);
+  t.build_debug = env_int("SMOE_CORR_BUILD_DEBUG", 0);
+  if (const char* e = getenv("SMOE_CORR_LOOKUP_CONV")) t.conv_lanes = e[0] == 'l';
+#else
+  (void)env_int;
+#endif
+  return t;
+}
+
+#ifdef SMOE_CROSSCHECK
+static Tuning g_tuning = read_tuning();           // the cross-check library may change it at run time
+#else
+static const Tuning g_tuning = read_tuning();     // dynamic initialisation == library load
+#endif
+const Tuning& tuning() { return g_tuning; }
 
 int validate_pyramid(const smoe_pyramid_t* p, const char* who) {
   SMOE_REQUIRE(p != nullptr, SMOE_ERR_INVALID_ARG, "%s: pyramid is NULL", who);
@@ -52,6 +80,20 @@ int validate_pyramid(const smoe_pyramid_t* p, const char* who) {
 }  // namespace smoe
 
 extern "C" {
+
+#ifdef SMOE_CROSSCHECK
+// Tests / probes: set one Tuning field by name (process-wide; not thread-safe by design).
+int smoe_corr_debug_set_tuning(const char* name, int value) {
+  using smoe::g_tuning;
+#define SMOE_FIELD(f) if (strcmp(name, #f) == 0) { g_tuning.f = value; return 0; }
+  SMOE_FIELD(pdl) SMOE_FIELD(fwd_kernel) SMOE_FIELD(px_tpb) SMOE_FIELD(px_split) SMOE_FIELD(px_ld256)
+  SMOE_FIELD(px_hint) SMOE_FIELD(lookup_tile) SMOE_FIELD(bwd_staged) SMOE_FIELD(bwd_split)
+  SMOE_FIELD(bwd_rowmod) SMOE_FIELD(build_pair) SMOE_FIELD(build_stages) SMOE_FIELD(build_debug)
+  SMOE_FIELD(conv_lanes)
+#undef SMOE_FIELD
+  return 1;
+}
+#endif
 
 int smoe_corr_abi_version(void) { return SMOE_CORR_ABI_VERSION; }
 

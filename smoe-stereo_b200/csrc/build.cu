@@ -705,17 +705,21 @@ static int launch_build_impl(const CUtensorMap& ta, const CUtensorMap& tb, const
 template <typename IT, typename OT>
 static int launch_build(const CUtensorMap& ta, const CUtensorMap& tb, const PyrDev& out, int num_levels, const BuildDims& dims, cudaStream_t st) {
   if (dims.kmajor) return launch_build_impl<IT, OT, false, true>(ta, tb, out, num_levels, dims, st);
-  return dims.pair ? launch_build_impl<IT, OT, true>(ta, tb, out, num_levels, dims, st)
-                   : launch_build_impl<IT, OT, false>(ta, tb, out, num_levels, dims, st);
+#ifdef SMOE_CROSSCHECK      // the CTA-pair variant (cta_group::2) measured no faster: cross-check build only
+  if (dims.pair) return launch_build_impl<IT, OT, true>(ta, tb, out, num_levels, dims, st);
+#endif
+  return launch_build_impl<IT, OT, false>(ta, tb, out, num_levels, dims, st);
 }
 
 }  // namespace smoe
 
 extern "C" {
 
+#ifdef SMOE_CROSSCHECK
 void smoe_corr_debug_set_timeline(void* device_buffer) {
   smoe::g_timeline = static_cast<long long*>(device_buffer);
 }
+#endif
 
 int64_t smoe_corr_build_workspace_bytes(int B, int C, int H, int W1, int W2, int in_dtype) {
   using namespace smoe;
@@ -804,10 +808,11 @@ int smoe_corr_build(const void* fmap1, const void* fmap2, int in_dtype, int B, i
   dims.W1 = W1; dims.W2 = W2; dims.C = C; dims.H = H; dims.BH = B * H;
   dims.kmajor = kmajor ? 1 : 0;
   dims.store_mask = (flags & SMOE_BUILD_SKIP_ODD_LEVELS) ? 0x5 : 0xF;
-  {
-    const char* e = getenv("SMOE_CORR_BUILD_PAIR");
-    dims.pair = (e && !kmajor) ? atoi(e) : 0;
-  }
+#ifdef SMOE_CROSSCHECK
+  dims.pair = kmajor ? 0 : tuning().build_pair;
+#else
+  dims.pair = 0;
+#endif
   dims.MT = (W1 + (dims.pair ? 2 : 1) * kBlockM - 1) / ((dims.pair ? 2 : 1) * kBlockM);
   dims.NT = (W2 + kBlockN - 1) / kBlockN;
   {
@@ -817,10 +822,7 @@ int smoe_corr_build(const void* fmap1, const void* fmap2, int in_dtype, int B, i
     if (dims.BN > kBlockN) dims.BN = kBlockN;
   }
   dims.debug = 0;
-  if (kProbes) {
-    const char* e = getenv("SMOE_CORR_BUILD_DEBUG");
-    dims.debug = e ? atoi(e) : 0;
-  }
+  if (kProbes) dims.debug = tuning().build_debug;
   {
     // B slabs (128 bytes of W2 each) one N tile needs -> bytes per stage -> ring depth
     const int slab = 128 / es;
@@ -828,8 +830,8 @@ int smoe_corr_build(const void* fmap1, const void* fmap2, int in_dtype, int B, i
     dims.stage_bytes = kStageABytes + (bn_cta + slab - 1) / slab * (kStageBBytes / (kBlockN / slab));
     dims.stages = (kMaxSmemBytes - kBuildSmemFixed) / dims.stage_bytes;
     if (dims.stages > kMaxStages) dims.stages = kMaxStages;
-    const char* e = getenv("SMOE_CORR_BUILD_STAGES");      // experiment switch
-    if (e && atoi(e) >= 2 && atoi(e) < dims.stages) dims.stages = atoi(e);
+    const int cap = tuning().build_stages;                  // experiment switch (cross-check build)
+    if (cap >= 2 && cap < dims.stages) dims.stages = cap;
   }
   CUtensorMap ta, tb;
   if (kmajor) {

@@ -258,8 +258,8 @@ static int encode(CUtensorMap* out, int rank, const void* base, const cuuint64_t
 extern "C" {
 
 int smoe_corr_build_bwd(const void* fmap1, const void* fmap2, int in_dtype, int B, int C, int H, int W1,
-                        int W2, const smoe_pyramid_t* grad_pyr, float denom, void* dfmap1, void* dfmap2,
-                        smoe_stream_t stream) {
+                        int W2, int64_t row_pitch1, int64_t row_pitch2, const smoe_pyramid_t* grad_pyr,
+                        float denom, void* dfmap1, void* dfmap2, smoe_stream_t stream) {
   using namespace smoe;
   if (int rc = validate_pyramid(grad_pyr, "build_bwd")) return rc;
   SMOE_REQUIRE(in_dtype == SMOE_DTYPE_F32 && grad_pyr->dtype == SMOE_DTYPE_F32, SMOE_ERR_UNSUPPORTED,
@@ -271,8 +271,10 @@ int smoe_corr_build_bwd(const void* fmap1, const void* fmap2, int in_dtype, int 
   SMOE_REQUIRE(denom > 0.f, SMOE_ERR_INVALID_ARG, "build_bwd: denom must be positive");
   if (B == 0 || H == 0 || W1 == 0 || W2 == 0) return SMOE_OK;
   SMOE_REQUIRE(fmap1 && fmap2 && dfmap1 && dfmap2, SMOE_ERR_INVALID_ARG, "build_bwd: NULL pointer");
-  SMOE_REQUIRE(W1 % 4 == 0 && W2 % 4 == 0, SMOE_ERR_UNSUPPORTED,
-               "build_bwd: W1=%d / W2=%d must be multiples of 4 (TMA 16-byte strides)", W1, W2);
+  SMOE_REQUIRE(row_pitch1 >= W1 && row_pitch2 >= W2 && row_pitch1 % 4 == 0 && row_pitch2 % 4 == 0,
+               SMOE_ERR_INVALID_ARG,
+               "build_bwd: row pitches %lld / %lld must be multiples of 4 elements (TMA 16-byte strides) "
+               "and >= W1=%d / W2=%d", (long long)row_pitch1, (long long)row_pitch2, W1, W2);
   SMOE_REQUIRE(aligned16(fmap1) && aligned16(fmap2) && aligned16(grad_pyr->level_ptr[0]) &&
                    (grad_pyr->pitch[0] * 4) % 16 == 0,
                SMOE_ERR_INVALID_ARG, "build_bwd: operands must be 16-byte aligned");
@@ -289,25 +291,25 @@ int smoe_corr_build_bwd(const void* fmap1, const void* fmap2, int in_dtype, int 
                         CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, "G/MN"))
       return rc;
   }
-  auto fmap_map = [&](CUtensorMap* m, const void* base, int W, const char* what) {
+  auto fmap_map = [&](CUtensorMap* m, const void* base, int W, int64_t Wp, const char* what) {
     const cuuint64_t gdim[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)B};
-    const cuuint64_t gstr[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)C * H * W * 4};
+    const cuuint64_t gstr[3] = {(cuuint64_t)Wp * 4, (cuuint64_t)H * Wp * 4, (cuuint64_t)C * H * Wp * 4};
     const cuuint32_t box[4] = {32u, 1u, (cuuint32_t)kBwdN, 1u};
     return encode(m, 4, base, gdim, gstr, box, CU_TENSOR_MAP_SWIZZLE_128B, what);
   };
-  if (int rc = fmap_map(&f1m, fmap1, W1, "fmap1")) return rc;
-  if (int rc = fmap_map(&f2m, fmap2, W2, "fmap2")) return rc;
+  if (int rc = fmap_map(&f1m, fmap1, W1, row_pitch1, "fmap1")) return rc;
+  if (int rc = fmap_map(&f2m, fmap2, W2, row_pitch2, "fmap2")) return rc;
   CUtensorMap d1m, d2m;
-  auto out_map = [&](CUtensorMap* m, void* base, int W, const char* what) {
+  auto out_map = [&](CUtensorMap* m, void* base, int W, int64_t Wp, const char* what) {
     const cuuint64_t gdim[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)B};
-    const cuuint64_t gstr[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)C * H * W * 4};
+    const cuuint64_t gstr[3] = {(cuuint64_t)Wp * 4, (cuuint64_t)H * Wp * 4, (cuuint64_t)C * H * Wp * 4};
     const cuuint32_t box[4] = {32u, 1u, 32u, 1u};
     return encode(m, 4, base, gdim, gstr, box, CU_TENSOR_MAP_SWIZZLE_NONE, what, false);
   };
   SMOE_REQUIRE(aligned16(dfmap1) && aligned16(dfmap2), SMOE_ERR_INVALID_ARG,
                "build_bwd: gradient outputs must be 16-byte aligned");
-  if (int rc = out_map(&d1m, dfmap1, W1, "dfmap1")) return rc;
-  if (int rc = out_map(&d2m, dfmap2, W2, "dfmap2")) return rc;
+  if (int rc = out_map(&d1m, dfmap1, W1, row_pitch1, "dfmap1")) return rc;
+  if (int rc = out_map(&d2m, dfmap2, W2, row_pitch2, "dfmap2")) return rc;
 
   BwdDims d;
   d.W1 = W1; d.W2 = W2; d.C = C; d.H = H; d.BH = B * H;

@@ -7,6 +7,9 @@
 #include <stdio.h>
 
 #include "../../include/smoe_corr.h"
+#ifdef SMOE_CROSSCHECK
+#include "xcheck_api.h"
+#endif
 
 namespace smoe {
 
@@ -40,12 +43,34 @@ inline int check_launch(const char* what) {
   return SMOE_OK;
 }
 
-// Programmatic dependent launch (PDL): the kernel may become resident while its predecessor in
-// the stream is still draining; it must execute pdl_wait() before touching global memory.
-// On B200 back-to-back lane-group lookups measured ~10% SLOWER with PDL, the thread-per-pixel
-// lookup ~6% faster (2.82 vs 3.01 us at cfg1; profiles/r01/README.md), so by default only launches
-// that ask for it (prefer_pdl) get the attribute.  SMOE_CORR_PDL=0 / 1 forces it off / on everywhere.
-int pdl_mode();   // api.cu: 0 never, 1 always, 2 where preferred
+// Launch-time tuning, read ONCE when the library is loaded (api.cu) -- never inside an entry point.
+// The product library honours a single documented switch, SMOE_CORR_PDL; every other field is a
+// compile-time default there.  The cross-check build (-DSMOE_CROSSCHECK, tests/tools only: it also
+// carries the superseded kernels as bit-exact checkers) lets the environment override them for A/B
+// measurements (tools/README.md).
+struct Tuning {
+  // Programmatic dependent launch: the kernel may become resident while its predecessor in the
+  // stream is still draining; it must execute pdl_wait() before touching global memory.  On B200
+  // back-to-back lane-group lookups measured ~10% SLOWER with PDL, the thread-per-pixel lookup ~6%
+  // faster (2.82 vs 3.01 us at cfg1; profiles/r01/README.md), so by default only launches that ask
+  // for it (prefer_pdl) get the attribute.  0 never, 1 always, 2 where preferred.
+  int pdl = 2;
+  int fwd_kernel = 0;      // 0 default (px) | 1 px, 16-byte loads | 2 pair | 3 vec | 4 px, 256-bit loads
+  int px_tpb = 32;         // pixels per CTA of the thread-per-pixel lookup
+  int px_split = 1;        // one thread per level pair
+  int px_ld256 = -1;       // 256-bit segment loads: -1 = for fp32 volumes beyond L2, 0 never, 1 always
+  int px_hint = 1;         // L2 eviction priorities of the streaming lookup (lookup.cu, PxHint)
+  int lookup_tile = 32;    // lane-group kernels: pixels per CTA
+  int bwd_staged = 0;      // first version of the batched backward (cross-check build only)
+  int bwd_split = 2;       // threads per (pixel, level) in lookup_bwd_lvl_kernel: 1, 2 or 3
+  int bwd_rowmod = 2;      // shared-memory row length of that kernel, modulo 32 banks
+  int build_pair = 0;      // CTA-pair build kernel (cross-check build only)
+  int build_stages = 0;    // cap of the operand ring depth (0 = fill shared memory)
+  int build_debug = 0;     // probe builds (-DSMOE_BUILD_PROBES)
+  int conv_lanes = 0;      // lane-group version of the fused lookup+conv (cross-check build only)
+};
+const Tuning& tuning();    // api.cu
+inline int pdl_mode() { return tuning().pdl; }
 
 // cluster_x > 1 launches thread-block clusters of that many CTAs along x (grid.x a multiple of it)
 template <typename... KArgs, typename... Args>

@@ -34,224 +34,10 @@ __device__ __forceinline__ uint32_t ptx_smem(const void* p) {
 constexpr int kTilePx = 32;       // pixels per CTA tile (one 128-byte line of fp32 outputs)
 constexpr int kFwdThreads = 128;  // 4 lanes per pixel
 
-// ----------------------------------------------------------------------------- forward (vector)
-// Shared "window space" tile: for every (level, pixel) the 4*EPL interpolated values
-// e[i] = lerp(v[i], v[i+1]) of the aligned chunks covering the pixel's window, plus the shift s
-// (window start inside the first chunk).  Output channel k of that level is e[s + k]: the
-// data-dependent shift is applied on the READ side, so the write side is one 16-byte store per
-// chunk and the output loop is `LDS [row + s + k]` with immediate k.  Row stride WIN+4 words keeps
-// the 16-byte alignment and spreads rows over banks (the kernel is issue/latency-bound at
-// L2-resident sizes, so instruction count matters more than the residual 2-4 way conflicts:
-// 416 -> ~290 SASS instructions per thread, profiles/r01/README.md).
-template <int EPL> struct WinTile {
-  static constexpr int kWin = 4 * EPL;
-  static constexpr int kStride = kWin + 4;                 // words per (level,pixel) row
-};
-
-template <typename VT, typename OT, int R, int NL, int TPX, bool STREAM>
-__global__ void __launch_bounds__(4 * TPX)
-lookup_fwd_vec_kernel(PyrDev pyr, const float* __restrict__ coords, long long coords_bstride,
-                      float coord_scale, OT* __restrict__ out, int HW, CoordUpd upd) {
-  constexpr int EPL = Vec16<VT>::N;          // elements per 16-byte chunk
-  constexpr int LOG_EPL = (EPL == 4) ? 2 : 3;
-  constexpr int RD = 2 * R + 1;
-  constexpr int QMAX = (EPL - 1 + 2 * R + 1) >> LOG_EPL;   // last chunk a window can reach
-  using Tile = WinTile<EPL>;
-  static_assert(EPL - 1 + 2 * R + 2 <= 4 * EPL, "window must fit the 4 chunks of a lane group");
-  __shared__ __align__(16) float s_win[NL][TPX * Tile::kStride];
-  __shared__ int s_shift[NL][TPX];
-
-  pdl_wait();                // coords / pyramid come from earlier kernels in the stream
-  const int tid = threadIdx.x;
-  const int p = tid >> 2, q = tid & 3;
-  const int b = blockIdx.y;
-  const int hw0 = blockIdx.x * TPX;
-  const int hw = hw0 + p;
-  const bool valid = hw < HW;
-  const float x0 = valid ? fetch_coord(coords, coords_bstride, upd, b, hw, q == 0) * coord_scale : 0.f;
-  const long long row = (long long)b * HW + hw;
-
-  float v[NL][EPL];
-  float dxs[NL];
-  float lscale = 1.0f;
-#pragma unroll
-  for (int l = 0; l < NL; ++l) {
-    int base;
-    split_coord(x0 * lscale, R, base, dxs[l]);
-    lscale *= 0.5f;
-    const int s = base & (EPL - 1);
-    const int ci = (base >> LOG_EPL) + q;          // arithmetic shift == floor division
-    if (q == 0) s_shift[l][p] = s;
-    const int width = pyr.width[l];
-    const unsigned nchunks = (unsigned)(width + EPL - 1) >> LOG_EPL;
-    // chunk q intersects the window iff q*EPL <= s + 2R+1; one unsigned compare checks 0 <= ci < nchunks
-    const bool need = valid && (q < QMAX || (q == QMAX && s + 2 * R + 1 >= QMAX * EPL)) &&
-                      (unsigned)ci < nchunks;
-#pragma unroll
-    for (int j = 0; j < EPL; ++j) v[l][j] = 0.f;
-    if (need) {
-      const VT* src = static_cast<const VT*>(pyr.ptr[l]) + row * pyr.pitch[l] + (long long)ci * EPL;
-      Vec16<VT>::template load<STREAM>(src, v[l]);
-      if (__builtin_expect((ci + 1) * EPL > width, 0)) {       // rare tail chunk: mask elements >= width
-#pragma unroll
-        for (int j = 0; j < EPL; ++j)
-          if (ci * EPL + j >= width) v[l][j] = 0.f;
-      }
-    }
-  }
-  pdl_launch_dependents();   // all loads are in flight: let the successor's CTAs become resident
-  float* my_row = &s_win[0][p * Tile::kStride + q * EPL];
-#pragma unroll
-  for (int l = 0; l < NL; ++l) {
-    const float nxt = __shfl_down_sync(0xffffffffu, v[l][0], 1);   // first element of chunk q+1
-    const float dx = dxs[l];
-    float e[EPL];
-    LerpChunk<OT, EPL>::run(v[l], nxt, dx, e);
-#pragma unroll
-    for (int h = 0; h < EPL / 4; ++h)
-      *reinterpret_cast<float4*>(my_row + l * (TPX * Tile::kStride) + 4 * h) =
-          make_float4(e[4 * h], e[4 * h + 1], e[4 * h + 2], e[4 * h + 3]);
-  }
-  __syncthreads();
-  // output phase: lane = pixel; a warp takes one (level, 32-pixel group) at a time, so every
-  // store instruction writes one full 128-byte line of one output channel
-  const int warp = tid >> 5, lane = tid & 31;
-  constexpr int kGroups = TPX / 32, kWarps = TPX / 8;
-  for (int item = warp; item < NL * kGroups; item += kWarps) {
-    const int l = item % NL, pg = item / NL;
-    const int pp = pg * 32 + lane;
-    if (hw0 + pp < HW) {
-      OT* dst = out + ((long long)b * (NL * RD) + l * RD) * HW + hw0 + pp;
-      const float* wrow = &s_win[l][pp * Tile::kStride] + s_shift[l][pp];
-#pragma unroll
-      for (int k = 0; k < RD; ++k) dst[(long long)k * HW] = from_float<OT>(wrow[k]);
-    }
-  }
-}
-
-// ------------------------------------------------------------------------- forward (level pairs)
-// Level i+1 is by construction the pair-average of level i (core/corr.py:122-125), and the 2r+2
-// taps of a pixel at level i+1 cover level-i indices [2*base_c, 2*base_c + 4r+3], which CONTAIN
-// the pixel's level-i window.  So the lookup reads ONE contiguous level-i segment (20 elements
-// for r=4) per level pair (0,1) and (2,3) -- half the scattered DRAM accesses and fewer sectors
-// than four separate 10-element windows -- and recomputes the coarse taps as (a+b)*0.5f, the same
-// fp32 operation the build epilogue used, so the result is bit-identical to reading levels 1/3.
-// 8 lanes per pixel: lane q fetches aligned chunk q of both segments (<= 6 chunks for fp32,
-// <= 4 for fp16).  Window-space tiles + read-side shifts as in lookup_fwd_vec_kernel.
-template <typename VT, typename OT, int R, int NP, int TPX, bool STREAM>
-__global__ void __launch_bounds__(8 * TPX)
-lookup_fwd_pair_kernel(PyrDev pyr, const float* __restrict__ coords, long long coords_bstride,
-                       float coord_scale, OT* __restrict__ out, int HW, CoordUpd upd) {
-  constexpr int EPL = Vec16<VT>::N;
-  constexpr int LOG_EPL = (EPL == 4) ? 2 : 3;
-  constexpr int RD = 2 * R + 1;
-  constexpr int SEG = 4 * R + 4;                              // fine elements under the coarse window
-  constexpr int NCH = (EPL - 2 + SEG + EPL - 1) / EPL;        // chunks a segment can span
-  static_assert(NCH <= 8, "segment must fit the 8 lanes of a pixel");
-  constexpr int FW = 8 * EPL;                                 // fine window-space words per pixel
-  constexpr int FS = FW + 4;                                  // row stride (bank spreading)
-  constexpr int CW = 4 * EPL;                                 // coarse window-space words per pixel
-  constexpr int CS = CW + 4;
-  __shared__ __align__(16) float s_fine[NP][TPX * FS];
-  __shared__ __align__(16) float s_coarse[NP][TPX * CS];
-  __shared__ int s_shift[2 * NP][TPX];
-
-  pdl_wait();
-  const int tid = threadIdx.x;
-  const int p = tid >> 3, q = tid & 7;
-  const int b = blockIdx.y;
-  const int hw0 = blockIdx.x * TPX;
-  const int hw = hw0 + p;
-  const bool valid = hw < HW;
-  const float x0 = valid ? fetch_coord(coords, coords_bstride, upd, b, hw, q == 0) * coord_scale : 0.f;
-  const long long row = (long long)b * HW + hw;
-
-  float v[NP][EPL];
-  float dxf[NP], dxc[NP];
-  int ci0[NP];
-  float lscale = 1.0f;
-#pragma unroll
-  for (int pr = 0; pr < NP; ++pr) {
-    const int lf = 2 * pr;
-    int basef, basec;
-    split_coord(x0 * lscale, R, basef, dxf[pr]);
-    split_coord(x0 * lscale * 0.5f, R, basec, dxc[pr]);
-    lscale *= 0.25f;
-    // the segment follows the coarse window unless the coordinate is out of the representable
-    // range (split_coord parks both far outside, everything masks to zero)
-    const int S = 2 * basec;
-    const int cs = S >> LOG_EPL;                               // first chunk of the segment
-    const int ci = cs + q;
-    ci0[pr] = cs;
-    if (q == 0) {
-      s_shift[2 * pr][p] = basef - (cs << LOG_EPL);            // fine tap k  -> fine tile index
-      s_shift[2 * pr + 1][p] = basec - (cs << (LOG_EPL - 1));  // coarse tap k -> coarse tile index
-    }
-    const int width = pyr.width[lf];
-    const int nchunks = (width + EPL - 1) >> LOG_EPL;
-    const bool need = valid && q < NCH && (ci << LOG_EPL) < S + SEG && ci >= 0 && ci < nchunks;
-#pragma unroll
-    for (int j = 0; j < EPL; ++j) v[pr][j] = 0.f;
-    if (need) {
-      const VT* src = static_cast<const VT*>(pyr.ptr[lf]) + row * pyr.pitch[lf] + (long long)ci * EPL;
-      Vec16<VT>::template load<STREAM>(src, v[pr]);
-      if ((ci + 1) * EPL > width) {
-#pragma unroll
-        for (int j = 0; j < EPL; ++j)
-          if (ci * EPL + j >= width) v[pr][j] = 0.f;
-      }
-    }
-  }
-  pdl_launch_dependents();
-#pragma unroll
-  for (int pr = 0; pr < NP; ++pr) {
-    const int wc = (2 * pr + 1 < pyr.num_levels) ? pyr.width[2 * pr + 1] : 0;
-    const int ci = ci0[pr] + q;
-    // coarse values owned by this lane: pair averages, zero where the coarse level has no column
-    float pc[EPL / 2];
-#pragma unroll
-    for (int j = 0; j < EPL / 2; ++j) {
-      const int cidx = ci * (EPL / 2) + j;
-      float a = (v[pr][2 * j] + v[pr][2 * j + 1]) * 0.5f;
-      if (sizeof(VT) == 2) a = __half2float(__float2half_rn(a));     // stored level is fp16
-      pc[j] = (cidx >= 0 && cidx < wc) ? a : 0.f;
-    }
-    const float nxt_f = __shfl_down_sync(0xffffffffu, v[pr][0], 1);
-    const float nxt_c = __shfl_down_sync(0xffffffffu, pc[0], 1);
-    float ef[EPL], ec[EPL / 2];
-    LerpChunk<OT, EPL>::run(v[pr], nxt_f, dxf[pr], ef);
-    LerpChunk<OT, EPL / 2>::run(pc, nxt_c, dxc[pr], ec);
-#pragma unroll
-    for (int h = 0; h < EPL / 4; ++h)
-      *reinterpret_cast<float4*>(&s_fine[pr][p * FS + (q * (EPL / 4) + h) * 4]) =
-          make_float4(ef[4 * h], ef[4 * h + 1], ef[4 * h + 2], ef[4 * h + 3]);
-    if (EPL == 4) {
-      *reinterpret_cast<float2*>(&s_coarse[pr][p * CS + q * 2]) = make_float2(ec[0], ec[1]);
-    } else {
-      *reinterpret_cast<float4*>(&s_coarse[pr][p * CS + q * 4]) =
-          make_float4(ec[0], ec[1], ec[EPL == 4 ? 0 : 2], ec[EPL == 4 ? 1 : 3]);
-    }
-  }
-  __syncthreads();
-  // output phase: lane = pixel; a warp takes one (level, 32-pixel group): full-line stores
-  const int warp = tid >> 5, lane = tid & 31;
-  constexpr int kGroups = TPX / 32, kWarps = TPX / 4;
-  const int NL = pyr.num_levels;
-  for (int item = warp; item < NL * kGroups; item += kWarps) {
-    const int l = item % NL, pg = item / NL;
-    const int pp = pg * 32 + lane;
-    if (hw0 + pp < HW) {
-      OT* dst = out + ((long long)b * (NL * RD) + l * RD) * HW + hw0 + pp;
-      const int sft = s_shift[l][pp];
-      const float* wrow = (l & 1) ? &s_coarse[l >> 1][pp * CS] : &s_fine[l >> 1][pp * FS];
-      const int lim = (l & 1) ? CW : FW;
-#pragma unroll
-      for (int k = 0; k < RD; ++k) {
-        const int e = sft + k;                                  // parked coordinates: out of tile -> 0
-        dst[(long long)k * HW] = from_float<OT>((e >= 0 && e < lim) ? wrow[e] : 0.f);
-      }
-    }
-  }
+// A pyramid that cannot stay L2-resident (126 MB L2, minus the lookup's own outputs) is read with
+// the streaming load variant (Vec16).
+static bool volume_exceeds_l2(const PyrDev& d, long long rows, int elem_bytes) {
+  return rows * d.pitch[0] * elem_bytes > (96ll << 20);   // (64 MB tried: worse for a 90 MB fp16 volume)
 }
 
 // ------------------------------------------------------------------- forward (thread per pixel)
@@ -273,13 +59,29 @@ lookup_fwd_pair_kernel(PyrDev pyr, const float* __restrict__ coords, long long c
 // SPLIT: blockDim.y = number of level pairs and each thread handles ONE pair of its pixel (half
 // the dependent instruction chain and registers per thread, twice the threads): for L2-resident
 // volumes, where the kernel is bound by the latency of that chain rather than by throughput.
-// LD256: fp32 volumes fetched with 256-bit loads (PxPair256; opt-in, SMOE_CORR_PX_LD256=1).
-template <typename VT, typename OT, int R, int NL, bool STREAM, bool SPLIT, bool LD256 = false>
+// LD256: fp32 volumes fetched with 256-bit loads (PxPair256): the default for volumes beyond L2.
+// HINT (LD256 + STREAM only): L2 eviction priorities.  A volume that streams from DRAM is dominated
+// by level 0 (16 of every 21 pyramid bytes the lookup reads per pixel row), whose segments are
+// single-use; level 2 is 4x smaller per row and the same lines are hit again by the next GRU
+// iteration.  bits 0-1: 1 = level-0 fills evict_first; 2 = also level-2 fills evict_last;
+// 3 = only level-2 evict_last.  bit 2: output stores evict_first (only when nothing reads them back).
+__device__ __forceinline__ void st_hint(float* p, float v, unsigned long long pol) {
+  asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_hint(__half* p, __half v, unsigned long long pol) {
+  asm volatile("st.global.L2::cache_hint.b16 [%0], %1, %2;" ::"l"(p), "h"(__half_as_ushort(v)), "l"(pol) : "memory");
+}
+
+template <typename VT, typename OT, int R, int NL, bool STREAM, bool SPLIT, bool LD256 = false, int HINT = 0>
 __global__ void __launch_bounds__(256)
 lookup_fwd_px_kernel(PyrDev pyr, const float* __restrict__ coords, long long coords_bstride,
                      float coord_scale, OT* __restrict__ out, int HW, CoordUpd upd) {
   static_assert(!LD256 || sizeof(VT) == 4, "256-bit segment loads are implemented for fp32 volumes");
+  static_assert(HINT == 0 || (LD256 && STREAM), "eviction hints ride on the streaming 256-bit loads");
   using Pair = typename std::conditional<LD256, PxPair256<STREAM>, PxPair<VT, STREAM>>::type;
+  constexpr int kHint0 = ((HINT & 3) == 1 || (HINT & 3) == 2) ? 1 : 0;
+  constexpr int kHint2 = (HINT & 3) >= 2 ? 2 : 0;
+  constexpr bool kOutEf = (HINT & 4) != 0;
   constexpr int RD = 2 * R + 1;
   constexpr int NP = (NL + 1) / 2;
   constexpr int NPT = SPLIT ? 1 : NP;                         // pairs per thread
@@ -302,10 +104,17 @@ lookup_fwd_px_kernel(PyrDev pyr, const float* __restrict__ coords, long long coo
     const VT* fine_row = static_cast<const VT*>(first ? pyr.ptr[0] : pyr.ptr[2]) +
                          row * (first ? pyr.pitch[0] : pyr.pitch[2]);
     pair[i].load(reinterpret_cast<const typename std::conditional<LD256, float, VT>::type*>(fine_row),
-                 first ? pyr.width[0] : pyr.width[2], x0 * (pr == 0 ? 1.0f : 0.25f));
+                 first ? pyr.width[0] : pyr.width[2], x0 * (pr == 0 ? 1.0f : 0.25f),
+                 pr == 0 ? kHint0 : kHint2);
   }
   pdl_launch_dependents();
 
+  unsigned long long pol = 0;
+  if (kOutEf) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  auto put = [&](OT* p, float v) {
+    if (kOutEf) st_hint(p, from_float<OT>(v), pol);
+    else *p = from_float<OT>(v);
+  };
   OT* dst = out + (long long)b * (NL * RD) * HW + hw;
 #pragma unroll
   for (int i = 0; i < NPT; ++i) {
@@ -316,12 +125,12 @@ lookup_fwd_px_kernel(PyrDev pyr, const float* __restrict__ coords, long long coo
       pair[i].template coarse<OT>((pr == 0 || NL < 4) ? pyr.width[1] : pyr.width[3], e);
       OT* d1 = dst + (long long)(lf + 1) * RD * HW;
 #pragma unroll
-      for (int k = 0; k < RD; ++k) d1[(long long)k * HW] = from_float<OT>(e[k]);
+      for (int k = 0; k < RD; ++k) put(d1 + (long long)k * HW, e[k]);
     }
     pair[i].template fine<OT>(e);
     OT* d0 = dst + (long long)lf * RD * HW;
 #pragma unroll
-    for (int k = 0; k < RD; ++k) d0[(long long)k * HW] = from_float<OT>(e[k]);
+    for (int k = 0; k < RD; ++k) put(d0 + (long long)k * HW, e[k]);
   }
 }
 
@@ -563,217 +372,106 @@ struct BatchedGeom {
   int num_levels;
 };
 
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
+#ifdef SMOE_CROSSCHECK
+#include "xcheck_lookup.cuh"
+#endif
 
-// elements per grad-tile row: a 16-byte multiple (cp.async) that is not a multiple of 32 words
-// elements per grad-tile row: 40 words for fp32 puts the 4 levels of a pixel (9 rows apart) 8 banks apart
-// and the 8 pixels of a warp in between: conflict-free tile reads; fp16 rows only need 16-byte alignment
-template <typename GT> struct BatchedTile { static constexpr int kStride = kTilePx + 32 / (int)sizeof(GT); };
-constexpr int kBatchedThreads = 256;   // two threads per (pixel, level): taps 0-4 and 5-9
-
-template <typename GT, int NL>
-__global__ void __launch_bounds__(kBatchedThreads)
-lookup_bwd_batched_kernel(const __grid_constant__ BwdBatch batch, const BatchedGeom geo,
-                          float* __restrict__ g0_out, long long g0_pitch, int HW, int accumulate) {
-  constexpr int R = 4, RD = 9;
-  constexpr int NC = NL * RD;
-  constexpr int kBatchedTileStride = BatchedTile<GT>::kStride;
-  constexpr int kTileBytes = NC * kBatchedTileStride * (int)sizeof(GT);   // one iteration's grad tile
-  extern __shared__ __align__(16) uint8_t s_raw[];
-  float* s_rows = reinterpret_cast<float*>(s_raw);                    // [kTilePx][rowlen]
-  uint8_t* s_tiles = s_raw + (size_t)kTilePx * geo.rowlen * 4;        // [stages][NC][kBatchedTileStride] GT
-  float* s_x = reinterpret_cast<float*>(s_tiles + kBatchedStages * kTileBytes);   // [stages][kTilePx]
-
-  pdl_launch_dependents();
-  pdl_wait();
-  const int tid = threadIdx.x;
-  const int b = blockIdx.y;
-  const int hw0 = blockIdx.x * kTilePx;
-  const int npx = min(kTilePx, HW - hw0);
-
-  auto issue = [&](int t, int buf) {
-    // grad tile: NC rows of kTilePx elements; 16-byte pieces, zero-filled past the end of the plane
-    constexpr int kPiecesPerRow = kTilePx * (int)sizeof(GT) / 16;
-    constexpr int kElemsPerPiece = 16 / (int)sizeof(GT);
-    const GT* g = static_cast<const GT*>(batch.gout[t]) + (long long)b * NC * HW + hw0;
-    for (int i = tid; i < NC * kPiecesPerRow; i += kBatchedThreads) {
-      const int c = i / kPiecesPerRow, e0 = (i - c * kPiecesPerRow) * kElemsPerPiece;
-      const int bytes = max(0, min(16, (npx - e0) * (int)sizeof(GT)));
-      const GT* src = g + (long long)c * HW + (bytes > 0 ? e0 : 0);
-      cp_async16(ptx_smem(s_tiles + buf * kTileBytes + (c * kBatchedTileStride + e0) * sizeof(GT)), src, bytes);
-    }
-    if (tid < kTilePx / 4) {
-      const int e0 = tid * 4;
-      const int bytes = max(0, min(16, (npx - e0) * 4));
-      const float* src = batch.coords[t] + (long long)b * batch.coords_bstride[t] + hw0 + (bytes > 0 ? e0 : 0);
-      cp_async16(ptx_smem(s_x + buf * kTilePx + e0), src, bytes);
-    }
-    cp_async_commit();
-  };
-
-  for (int t = 0; t < kBatchedStages; ++t) {
-    if (t < batch.T) issue(t, t); else cp_async_commit();     // exactly one group per slot
-  }
-  // rows start from zero (or from the existing level-0 gradient when accumulating)
-  for (int i = tid; i < kTilePx * geo.rowlen / 4; i += kBatchedThreads)
-    reinterpret_cast<float4*>(s_rows)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (accumulate) {
-    __syncthreads();
-    for (int pp = 0; pp < npx; ++pp)
-      for (int j = tid; j < geo.width[0]; j += kBatchedThreads)
-        s_rows[pp * geo.rowlen + j] = g0_out[((long long)b * HW + hw0 + pp) * g0_pitch + j];
-  }
-
-  // one thread per (pixel, level): its 2r+2 taps are contiguous in the shared-memory row, so there
-  // is no 16-byte chunking (that only matters for global memory) and no idle slot
-  const int p = (tid >> 2) & (kTilePx - 1), l = tid & 3, half = tid >> 7;   // half: taps 0-4 / 5-9
-  const bool active = p < npx && l < NL;
-  float* rowl = s_rows + p * geo.rowlen + geo.off[l];
-  const int width = geo.width[l];
-  const float lscale = 1.0f / (float)(1 << l);
-  for (int t = 0; t < batch.T; ++t) {
-    const int buf = t % kBatchedStages;
-    // groups committed so far: kBatchedStages + (t-1) (the refill of this iteration comes after the
-    // wait), so at most kBatchedStages-2 may still be pending for tile t to have landed
-    cp_async_wait<kBatchedStages - 2>();
-    __syncthreads();                       // tile t visible to everyone; everyone finished tile t-1
-    // refill the buffer consumed in the PREVIOUS iteration (one barrier per iteration suffices)
-    if (t >= 1) {
-      if (t - 1 + kBatchedStages < batch.T) issue(t - 1 + kBatchedStages, (t - 1) % kBatchedStages);
-      else cp_async_commit();
-    }
-    if (active) {
-      const GT* tl = reinterpret_cast<const GT*>(s_tiles + buf * kTileBytes) + (l * RD) * kBatchedTileStride + p;
-      int base;
-      float dx;
-      split_coord(s_x[buf * kTilePx + p] * lscale, R, base, dx);
-      // this thread's 5 taps: all shared-memory loads first, then the math, then the stores, so
-      // the read-modify-writes do not serialise on the shared-memory latency
-      const int t0 = half * 5;
-      float cur[5], g[6];
-      bool ok[5];
-      g[0] = half ? to_float(tl[(t0 - 1) * kBatchedTileStride]) : 0.f;
-#pragma unroll
-      for (int k = 0; k < 5; ++k) {
-        g[k + 1] = (t0 + k < RD) ? to_float(tl[(t0 + k) * kBatchedTileStride]) : 0.f;
-        const int idx = base + t0 + k;
-        ok[k] = (unsigned)idx < (unsigned)width;
-        cur[k] = ok[k] ? rowl[idx] : 0.f;
-      }
-#pragma unroll
-      for (int k = 0; k < 5; ++k)
-        cur[k] += BwdTap<float>::eval(g[k], g[k + 1], t0 + k > 0, t0 + k < RD, dx);
-#pragma unroll
-      for (int k = 0; k < 5; ++k)
-        if (ok[k]) rowl[base + t0 + k] = cur[k];
-    }
-  }
-  __syncthreads();                         // all scatters done before the fold reads the rows
-  // fold the levels in shared memory and write level 0 (same chain as fold_grad_*_kernel);
-  // which coarser levels cover column j depends on j only, so it is resolved once per column
-  const int w0 = geo.width[0];
-  for (int j = tid; j < w0; j += kBatchedThreads) {
-    int top = 0;
-    for (int lv = 1; lv < NL; ++lv) {
-      if ((j >> lv) >= geo.width[lv]) break;
-      top = lv;
-    }
-    const int i1 = geo.off[1] + (j >> 1), i2 = geo.off[2] + (j >> 2), i3 = geo.off[3] + (j >> 3);
-    float* out = g0_out + ((long long)b * HW + hw0) * g0_pitch + j;
-    for (int pp = 0; pp < npx; ++pp) {
-      const float* rowp = s_rows + pp * geo.rowlen;
-      float tsum = 0.f;
-      if (top >= 3) tsum = rowp[i3];
-      if (top >= 2) tsum = rowp[i2] + 0.5f * tsum;
-      if (top >= 1) tsum = rowp[i1] + 0.5f * tsum;
-      out[(long long)pp * g0_pitch] = rowp[j] + 0.5f * tsum;
-    }
-  }
-}
-
-// Second version of the batched backward: warp = pyramid level, lane = pixel of the 32-pixel tile.
+// Batched backward, current version: warp = (pyramid level, tap group), lane = pixel of the 32-pixel tile.
 // The gradient rows of a pixel are private to it and the levels occupy disjoint parts of the row,
 // so the T iterations need NO barrier and no shared-memory staging of the gradient tiles: each warp
-// streams its 9 gradient channels (+ the coordinate) of iteration t straight from global memory
-// into registers -- lane = pixel makes every load one coalesced line -- two iterations ahead of
-// the one it is scattering.  One coordinate split per (pixel, level, iteration) instead of two,
-// no cp.async address arithmetic, no per-iteration __syncthreads: ~2.2x fewer warp-instructions
-// than lookup_bwd_batched_kernel, and no 16-byte alignment requirement on the gradient planes.
-// Same accumulation order per element (iterations ascending) => bit-identical results.
-template <typename GT, int NL>
-__global__ void __launch_bounds__(128)
+// streams the gradient channels it needs (+ the coordinate) of iteration t straight from global
+// memory into registers -- lane = pixel makes every load one coalesced line -- several iterations
+// ahead of the one it is scattering.  No cp.async address arithmetic, no per-iteration
+// __syncthreads, no alignment requirement on the gradient planes.
+// NS = threads per (pixel, level): the 2r+2 = 10 window elements of a (pixel, level) are split into
+// NS disjoint tap groups handled by different warps (NS = 2: taps 0-4 / 5-9).  The groups touch
+// disjoint shared-memory words, so there is still no race and no barrier; every element still
+// receives exactly one contribution per iteration, iterations ascending => bit-identical results
+// for every NS.  What it buys: the kernel is bound by the dependent shared-memory
+// read-modify-write chain of each warp at an occupancy that the 45 KB of gradient rows per tile
+// cap at 5 CTAs per SM (profiles/r01/README.md); NS = 2 doubles the warps per SM (20 -> 40) for
+// the same shared memory and halves each chain.  Cost: the channel at a group boundary is loaded
+// by two warps (10 instead of 9 channel loads per level; an L1 hit).
+template <int NS> struct BwdSplit;
+template <> struct BwdSplit<1> { static constexpr int NT = 10, kDepth = 5, kMinBlocks = 5; };
+template <> struct BwdSplit<2> { static constexpr int NT = 5, kDepth = 3, kMinBlocks = 5; };   // <= 51 registers
+template <> struct BwdSplit<3> { static constexpr int NT = 4, kDepth = 3, kMinBlocks = 3; };
+
+template <typename GT, int NL, int NS>
+__global__ void __launch_bounds__(128 * NS, BwdSplit<NS>::kMinBlocks)
 lookup_bwd_lvl_kernel(const __grid_constant__ BwdBatch batch, const BatchedGeom geo,
                       float* __restrict__ g0_out, long long g0_pitch, int HW, int accumulate) {
-#ifndef SMOE_BWD_LVL_DEPTH
-#define SMOE_BWD_LVL_DEPTH 5
-#endif
-  constexpr int R = 4, RD = 9, NC = NL * RD, kDepth = SMOE_BWD_LVL_DEPTH;   // register ring: kDepth-1 iterations in flight
+  constexpr int R = 4, RD = 9, NC = NL * RD;
+  constexpr int NT = BwdSplit<NS>::NT;            // window elements per thread (at most)
+  constexpr int kDepth = BwdSplit<NS>::kDepth;    // register ring: kDepth-1 iterations in flight
+  constexpr int kThreads = 128 * NS;
   extern __shared__ __align__(16) uint8_t s_raw[];
   float* s_rows = reinterpret_cast<float*>(s_raw);                    // [kTilePx][rowlen]
 
   pdl_launch_dependents();
   pdl_wait();
   const int tid = threadIdx.x;
-  const int l = tid >> 5, lane = tid & 31;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int l = warp & 3, part = warp >> 2;
   const int b = blockIdx.y;
   const int hw0 = blockIdx.x * kTilePx;
   const int npx = min(kTilePx, HW - hw0);
 
-  for (int i = tid; i < kTilePx * geo.rowlen / 4; i += 128)
+  for (int i = tid; i < kTilePx * geo.rowlen / 4; i += kThreads)
     reinterpret_cast<float4*>(s_rows)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (accumulate) {
     __syncthreads();
     for (int pp = 0; pp < npx; ++pp)
-      for (int j = tid; j < geo.width[0]; j += 128)
+      for (int j = tid; j < geo.width[0]; j += kThreads)
         s_rows[pp * geo.rowlen + j] = g0_out[((long long)b * HW + hw0 + pp) * g0_pitch + j];
   }
   __syncthreads();
 
   if (l < NL && lane < npx) {
-    float* rowl = s_rows + lane * geo.rowlen + geo.off[l];
+    // this thread's window elements [t0, t0 + nt) and the gradient channels [t0-1, t0+nt-1] they use
+    const int t0 = NS == 1 ? 0 : (NS == 2 ? 5 * part : (part == 0 ? 0 : 3 * part + 1));
+    const int nt = NS == 3 ? (part == 0 ? 4 : 3) : NT;
+    float* rowl = s_rows + lane * geo.rowlen + geo.off[l] + t0;
     const unsigned width = (unsigned)geo.width[l];
     const float lscale = 1.0f / (float)(1 << l);
     const long long gofs = ((long long)b * NC + l * RD) * HW + hw0 + lane;
-    float g[kDepth][RD], x[kDepth];
-    auto load = [&](int t, float (&gt)[RD], float& xt) {
+    float g[kDepth][NT + 1], x[kDepth];
+    auto load = [&](int t, float (&gt)[NT + 1], float& xt) {
       const GT* gp = static_cast<const GT*>(batch.gout[t]) + gofs;
 #pragma unroll
-      for (int k = 0; k < RD; ++k) gt[k] = to_float(__ldg(gp + (long long)k * HW));
+      for (int j = 0; j <= NT; ++j) {                 // gt[j] = channel t0-1+j (0 where it does not exist)
+        const int c = t0 - 1 + j;
+        gt[j] = (c >= 0 && c < RD && j <= nt) ? to_float(__ldg(gp + (long long)c * HW)) : 0.f;
+      }
       xt = __ldg(batch.coords[t] + (long long)b * batch.coords_bstride[t] + hw0 + lane);
     };
-    auto scatter = [&](const float (&gt)[RD], float xt) {
+    auto scatter = [&](const float (&gt)[NT + 1], float xt) {
       int base;
       float dx;
       split_coord(xt * lscale, R, base, dx);
       // (a shared-memory atomicAdd per tap compiles to an ATOMS.CAST.SPIN loop on sm_100a: no gain)
-      float cur[RD + 1];
-      bool ok[RD + 1];
+      float cur[NT];
+      bool ok[NT];
 #pragma unroll
-      for (int k = 0; k <= RD; ++k) {                 // all shared-memory loads first
-        ok[k] = (unsigned)(base + k) < width;
+      for (int k = 0; k < NT; ++k) {                  // all shared-memory loads first
+        ok[k] = k < nt && (unsigned)(base + t0 + k) < width;
         cur[k] = ok[k] ? rowl[base + k] : 0.f;
       }
 #pragma unroll
-      for (int k = 0; k <= RD; ++k)
-        cur[k] += BwdTap<float>::eval(k > 0 ? gt[k - 1] : 0.f, k < RD ? gt[k] : 0.f, k > 0, k < RD, dx);
+      for (int k = 0; k < NT; ++k)
+        cur[k] += BwdTap<float>::eval(gt[k], gt[k + 1], t0 + k > 0, t0 + k < RD, dx);
 #pragma unroll
-      for (int k = 0; k <= RD; ++k)
+      for (int k = 0; k < NT; ++k)
         if (ok[k]) rowl[base + k] = cur[k];
     };
     const int T = batch.T;
 #pragma unroll
     for (int u = 0; u < kDepth - 1; ++u)
       if (u < T) load(u, g[u], x[u]);
-    for (int t0 = 0; t0 < T; t0 += kDepth) {
+    for (int tt = 0; tt < T; tt += kDepth) {
 #pragma unroll
       for (int u = 0; u < kDepth; ++u) {
-        const int t = t0 + u;
+        const int t = tt + u;
         if (t < T) {
           if (t + kDepth - 1 < T) load(t + kDepth - 1, g[(u + kDepth - 1) % kDepth], x[(u + kDepth - 1) % kDepth]);
           scatter(g[u], x[u]);
@@ -783,7 +481,7 @@ lookup_bwd_lvl_kernel(const __grid_constant__ BwdBatch batch, const BatchedGeom 
   }
   __syncthreads();                         // all scatters done before the fold reads the rows
   const int w0 = geo.width[0];
-  for (int j = tid; j < w0; j += 128) {
+  for (int j = tid; j < w0; j += kThreads) {
     int top = 0;
     for (int lv = 1; lv < NL; ++lv) {
       if ((j >> lv) >= geo.width[lv]) break;
@@ -878,6 +576,24 @@ fold_grad_scalar_kernel(PyrDev gp, long long rows) {
   }
 }
 
+// ----------------------------------------------------------------------------------- fill levels
+// level i[row, j] = (level i-1[row, 2j] + level i-1[row, 2j+1]) * 0.5 -- the build epilogue's own
+// arithmetic (fp32 sum, one rounding to the storage type), for the levels a build with
+// SMOE_BUILD_SKIP_ODD_LEVELS left out.  One thread per output element, coalesced along j.
+template <typename VT>
+__global__ void __launch_bounds__(256)
+fill_level_kernel(const VT* __restrict__ prev, long long prev_pitch, VT* __restrict__ dst, long long dst_pitch,
+                  int width, long long total) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long row = i / width;
+  const int j = (int)(i - row * width);
+  const VT* p = prev + row * prev_pitch + 2 * j;
+  dst[row * dst_pitch + j] = from_float<VT>((to_float(p[0]) + to_float(p[1])) * 0.5f);
+}
+
 // --------------------------------------------------------------------------------- dispatch
 bool pyramid_vec_ok(const smoe_pyramid_t* p) {   // also used by lookup_conv.cu
   const int es = dtype_size(p->dtype);
@@ -891,96 +607,75 @@ bool pyramid_vec_ok(const smoe_pyramid_t* p) {   // also used by lookup_conv.cu
   return true;
 }
 
-// Pixels per CTA (32 / 64; 4 lanes per pixel).  SMOE_CORR_LOOKUP_TILE overrides for experiments.
-static int pick_fwd_tile(long long px) {
-  static const int forced = [] { const char* e = getenv("SMOE_CORR_LOOKUP_TILE"); return e ? atoi(e) : 0; }();
-  if (forced == 32 || forced == 64) return forced;
-  (void)px;
-  return 32;   // measured best at every size tried (cfg1: 3.65/3.80/4.04 us, cfg3: 32.8/33.7/35.5 us)
-}
-
-// A pyramid that cannot stay L2-resident (126 MB L2, minus the lookup's own outputs) is read with
-// the streaming load variant (Vec16).
-static bool volume_exceeds_l2(const PyrDev& d, long long rows, int elem_bytes) {
-  return rows * d.pitch[0] * elem_bytes > (96ll << 20);   // (64 MB tried: worse for a 90 MB fp16 volume)
-}
-
-template <typename VT, typename OT, int NL>
-static void launch_fwd_vec(const PyrDev& d, const float* coords, long long cbs, float cs, void* out,
-                           int HW, int B, cudaStream_t st, const CoordUpd& upd) {
-  int tile = pick_fwd_tile((long long)HW * B);
-  if (tile != 64) tile = 32;
-  dim3 grid((HW + tile - 1) / tile, B);
-  const bool big = volume_exceeds_l2(d, (long long)HW * B, (int)sizeof(VT));
-#define SMOE_LAUNCH_FWD(TPX, STREAM)                                                               \
-  launch_kernel(lookup_fwd_vec_kernel<VT, OT, 4, NL, TPX, STREAM>, grid, dim3(4 * TPX), 0, st, d,  \
-                coords, cbs, cs, static_cast<OT*>(out), HW, upd)
-  if (tile == 64) {
-    if (big) SMOE_LAUNCH_FWD(64, true); else SMOE_LAUNCH_FWD(64, false);
-  } else {
-    if (big) SMOE_LAUNCH_FWD(32, true); else SMOE_LAUNCH_FWD(32, false);
-  }
-#undef SMOE_LAUNCH_FWD
-}
-
-static const bool g_no_pair = getenv("SMOE_CORR_NO_PAIR_LOOKUP") != nullptr;      // A/B switches
-static const bool g_force_pair = getenv("SMOE_CORR_FORCE_PAIR_LOOKUP") != nullptr;
-
-template <typename VT, typename OT, int NP>
-static void launch_fwd_pair(const PyrDev& d, const float* coords, long long cbs, float cs, void* out,
-                            int HW, int B, cudaStream_t st, const CoordUpd& upd) {
-  constexpr int TPX = 32;
-  dim3 grid((HW + TPX - 1) / TPX, B);
-  const bool big = volume_exceeds_l2(d, (long long)HW * B, (int)sizeof(VT));
-  if (big)
-    launch_kernel(lookup_fwd_pair_kernel<VT, OT, 4, NP, TPX, true>, grid, dim3(8 * TPX), 0, st, d, coords,
-                  cbs, cs, static_cast<OT*>(out), HW, upd);
-  else
-    launch_kernel(lookup_fwd_pair_kernel<VT, OT, 4, NP, TPX, false>, grid, dim3(8 * TPX), 0, st, d, coords,
-                  cbs, cs, static_cast<OT*>(out), HW, upd);
-}
-
-// SMOE_CORR_LOOKUP_KERNEL=px|pair|vec forces one forward kernel (A/B experiments, parity tests)
-static const int g_fwd_kernel_env = [] {
-  const char* e = getenv("SMOE_CORR_LOOKUP_KERNEL");
-  if (!e) return 0;
-  return e[0] == 'p' && e[1] == 'x' ? 1 : (e[0] == 'p' ? 2 : (e[0] == 'v' ? 3 : 0));
-}();
+#ifdef SMOE_CROSSCHECK
 static thread_local int g_fwd_kernel_tls = -1;       // smoe_corr_debug_set_lookup_kernel
-#define g_fwd_kernel (g_fwd_kernel_tls >= 0 ? g_fwd_kernel_tls : g_fwd_kernel_env)
+static int fwd_kernel_choice() { return g_fwd_kernel_tls >= 0 ? g_fwd_kernel_tls : tuning().fwd_kernel; }
+constexpr bool kXcheck = true;
+#else
+static int fwd_kernel_choice() { return 0; }
+constexpr bool kXcheck = false;
+#endif
+constexpr int kDefaultPxHint = 1;        // level-0 fills evict_first (Tuning::px_hint)
+constexpr int kDefaultBwdSplit = 2;      // Tuning::bwd_split
 
-// experiment switches for the thread-per-pixel kernel: pixels per CTA, one thread per level pair
-static const int g_px_tpb = [] { const char* e = getenv("SMOE_CORR_PX_TPB"); return e ? atoi(e) : 0; }();
-static const int g_px_split = [] { const char* e = getenv("SMOE_CORR_PX_SPLIT"); return e ? atoi(e) : -1; }();
+// The 256-bit path reads whole 32-byte chunks aligned in MEMORY: the first chunk of a level may
+// begin 16 bytes before the level and the last may end 16 bytes after its row.  That stays inside
+// the pixel's own allocation iff level 0 is 32-byte aligned with a 32-byte-multiple pitch, and
+// level 2 either is too or lies inside level 0's row span with the same pitch (the fused layout of
+// smoe_corr_pyramid_layout, where padding follows every level).
+bool pyramid_ld256_ok(const PyrDev& d, int NL) {   // also used by lookup_conv.cu
+  auto a32 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31) == 0; };
+  if (!a32(d.ptr[0]) || (d.pitch[0] * 4) % 32 != 0) return false;
+  if (d.pitch[0] < (d.width[0] + 7) / 8 * 8) return false;
+  if (NL <= 2) return true;
+  if (a32(d.ptr[2]) && (d.pitch[2] * 4) % 32 == 0 && d.pitch[2] >= (d.width[2] + 7) / 8 * 8) return true;
+  const char* p0 = static_cast<const char*>(d.ptr[0]);
+  const char* p2 = static_cast<const char*>(d.ptr[2]);
+  return d.pitch[2] == d.pitch[0] && p2 >= p0 + 16 &&
+         p2 + ((long long)d.width[2] + 4) * 4 <= p0 + d.pitch[0] * 4;
+}
 
 template <typename VT, typename OT, int NL>
 static void launch_fwd_px(const PyrDev& d, const float* coords, long long cbs, float cs, void* out,
                           int HW, int B, cudaStream_t st, const CoordUpd& upd) {
   constexpr int NP = (NL + 1) / 2;
+  const Tuning& tn = tuning();
+  const int which = fwd_kernel_choice();
   const bool big = volume_exceeds_l2(d, (long long)HW * B, (int)sizeof(VT));
   // measured (tools/px_sweep.sh, bench.py): 32 pixels per CTA and one thread per level pair
   // everywhere -- beyond L2 (cfg2 10.2 -> 8.9 us, cfg3 fp16 18.6 -> 12.4 us), for fp16 volumes
   // (cfg1 3.40 -> 3.16 us) and, inside a real step (cold coordinates, distinct output buffers),
-  // for L2-resident fp32 volumes too: 3.38 -> 3.10 us per lookup of the cfg1 bench step, although
-  // a lookups-only graph with warm coordinates had shown 3.02 vs 3.08 us
-  const bool split = NP > 1 && (g_px_split >= 0 ? g_px_split != 0 : true);
-  int tpb = (g_px_tpb == 32 || g_px_tpb == 64 || g_px_tpb == 128) ? g_px_tpb : 32;
+  // for L2-resident fp32 volumes too: 3.38 -> 3.10 us per lookup of the cfg1 bench step
+  const bool split = NP > 1 && (!kXcheck || tn.px_split != 0);
+  const int tpb = (kXcheck && (tn.px_tpb == 64 || tn.px_tpb == 128)) ? tn.px_tpb : 32;
   dim3 grid((HW + tpb - 1) / tpb, B);
   OT* o = static_cast<OT*>(out);
   if constexpr (sizeof(VT) == 4 && sizeof(OT) == 4) {
     // 256-bit segment loads for fp32 volumes that stream from DRAM (tools/px256_check.py, 32 distinct
     // outputs per graph: cfg2 12.3 -> 8.4 us, cfg3 24.2 -> 20.5 us; L2-resident cfg1 3.08 -> 3.15 us,
-    // so those keep the 16-byte loads).  SMOE_CORR_PX_LD256=1 / 0 forces them on / off.  Level-0 rows
-    // must be 32-byte aligned (the first chunk of a level may start 16 bytes before it, which is
-    // only inside the pixel row for levels > 0).
-    static const int env256 = [] { const char* e = getenv("SMOE_CORR_PX_LD256"); return e ? (e[0] != '0' ? 1 : 0) : -1; }();
-    const bool ok256 = (reinterpret_cast<uintptr_t>(d.ptr[0]) & 31) == 0 && (d.pitch[0] * 4) % 32 == 0;
-    const bool want256 = g_fwd_kernel == 4 || (g_fwd_kernel == 0 && (env256 >= 0 ? env256 == 1 : big));
-    if (want256 && ok256) {
+    // so those keep the 16-byte loads)
+    const bool want256 = which == 4 || (which == 0 && (tn.px_ld256 >= 0 ? tn.px_ld256 == 1 : big));
+    if (want256 && pyramid_ld256_ok(d, NL)) {
       constexpr bool kSplit = NP > 1;
       dim3 block(tpb, kSplit ? NP : 1);
-      if (big) launch_kernel_pdl(lookup_fwd_px_kernel<VT, OT, 4, NL, true, kSplit, true>, grid, block, 0, st, d, coords, cbs, cs, o, HW, upd);
-      else launch_kernel_pdl(lookup_fwd_px_kernel<VT, OT, 4, NL, false, kSplit, true>, grid, block, 0, st, d, coords, cbs, cs, o, HW, upd);
+      if (!big) {
+        launch_kernel_pdl(lookup_fwd_px_kernel<VT, OT, 4, NL, false, kSplit, true>, grid, block, 0, st, d, coords, cbs, cs, o, HW, upd);
+        return;
+      }
+#define SMOE_PX256(H) launch_kernel_pdl(lookup_fwd_px_kernel<VT, OT, 4, NL, true, kSplit, true, H>, grid, block, 0, st, d, coords, cbs, cs, o, HW, upd)
+      if constexpr (kXcheck) {
+        switch (tn.px_hint) {
+          case 0: SMOE_PX256(0); break;
+          case 2: SMOE_PX256(2); break;
+          case 3: SMOE_PX256(3); break;
+          case 5: SMOE_PX256(5); break;
+          case 6: SMOE_PX256(6); break;
+          default: SMOE_PX256(kDefaultPxHint); break;
+        }
+      } else {
+        SMOE_PX256(kDefaultPxHint);
+      }
+#undef SMOE_PX256
       return;
     }
   }
@@ -989,7 +684,7 @@ static void launch_fwd_px(const PyrDev& d, const float* coords, long long cbs, f
     dim3 block(tpb, NP);
     if (big) launch_kernel_pdl(lookup_fwd_px_kernel<VT, OT, 4, NLS, true, true>, grid, block, 0, st, d, coords, cbs, cs, o, HW, upd);
     else launch_kernel_pdl(lookup_fwd_px_kernel<VT, OT, 4, NLS, false, true>, grid, block, 0, st, d, coords, cbs, cs, o, HW, upd);
-  } else {
+  } else if constexpr (NP == 1 || kXcheck) {
     dim3 block(tpb);
     if (big) launch_kernel_pdl(lookup_fwd_px_kernel<VT, OT, 4, NL, true, false>, grid, block, 0, st, d, coords, cbs, cs, o, HW, upd);
     else launch_kernel_pdl(lookup_fwd_px_kernel<VT, OT, 4, NL, false, false>, grid, block, 0, st, d, coords, cbs, cs, o, HW, upd);
@@ -999,33 +694,29 @@ static void launch_fwd_px(const PyrDev& d, const float* coords, long long cbs, f
 template <typename VT, typename OT>
 static void dispatch_fwd_vec(int NL, const PyrDev& d, const float* coords, long long cbs, float cs,
                              void* out, int HW, int B, cudaStream_t st, const CoordUpd& upd) {
-  // Default: the thread-per-pixel kernel (faster than both lane-group kernels at every size and
-  // dtype measured, tools/lookup_kernels_probe.py).  The lane-group kernels stay selectable
-  // (smoe_corr_debug_set_lookup_kernel / SMOE_CORR_LOOKUP_KERNEL) as bit-exact cross-checks.
-  if (g_fwd_kernel == 0 || g_fwd_kernel == 1 || g_fwd_kernel == 4) {
+#ifdef SMOE_CROSSCHECK
+  // the lane-group kernels, selectable as bit-exact cross-checks (smoe_corr_debug_set_lookup_kernel)
+  const int which = fwd_kernel_choice();
+  if (which == 2 || which == 3) {
+    if (which == 2 && (NL == 2 || NL == 4)) {
+      if (NL == 4) launch_fwd_pair<VT, OT, 2>(d, coords, cbs, cs, out, HW, B, st, upd);
+      else launch_fwd_pair<VT, OT, 1>(d, coords, cbs, cs, out, HW, B, st, upd);
+      return;
+    }
     switch (NL) {
-      case 1: launch_fwd_px<VT, OT, 1>(d, coords, cbs, cs, out, HW, B, st, upd); break;
-      case 2: launch_fwd_px<VT, OT, 2>(d, coords, cbs, cs, out, HW, B, st, upd); break;
-      case 3: launch_fwd_px<VT, OT, 3>(d, coords, cbs, cs, out, HW, B, st, upd); break;
-      default: launch_fwd_px<VT, OT, 4>(d, coords, cbs, cs, out, HW, B, st, upd); break;
+      case 1: launch_fwd_vec<VT, OT, 1>(d, coords, cbs, cs, out, HW, B, st, upd); break;
+      case 2: launch_fwd_vec<VT, OT, 2>(d, coords, cbs, cs, out, HW, B, st, upd); break;
+      case 3: launch_fwd_vec<VT, OT, 3>(d, coords, cbs, cs, out, HW, B, st, upd); break;
+      default: launch_fwd_vec<VT, OT, 4>(d, coords, cbs, cs, out, HW, B, st, upd); break;
     }
     return;
   }
-  // Volumes that stream from DRAM: two contiguous segments per pixel instead of four windows
-  // (cfg3: 31.3 -> 26.8 us).  L2-resident volumes stay on the 4-lane kernel (3.65 vs 4.04 us at
-  // cfg1: that regime is latency-bound and the pair kernel does more work per pixel).
-  const bool pair = (volume_exceeds_l2(d, (long long)HW * B, (int)sizeof(VT)) || g_force_pair ||
-                     g_fwd_kernel == 2) && g_fwd_kernel != 3;
-  if (!g_no_pair && pair && (NL == 2 || NL == 4)) {
-    if (NL == 4) launch_fwd_pair<VT, OT, 2>(d, coords, cbs, cs, out, HW, B, st, upd);
-    else launch_fwd_pair<VT, OT, 1>(d, coords, cbs, cs, out, HW, B, st, upd);
-    return;
-  }
+#endif
   switch (NL) {
-    case 1: launch_fwd_vec<VT, OT, 1>(d, coords, cbs, cs, out, HW, B, st, upd); break;
-    case 2: launch_fwd_vec<VT, OT, 2>(d, coords, cbs, cs, out, HW, B, st, upd); break;
-    case 3: launch_fwd_vec<VT, OT, 3>(d, coords, cbs, cs, out, HW, B, st, upd); break;
-    default: launch_fwd_vec<VT, OT, 4>(d, coords, cbs, cs, out, HW, B, st, upd); break;
+    case 1: launch_fwd_px<VT, OT, 1>(d, coords, cbs, cs, out, HW, B, st, upd); break;
+    case 2: launch_fwd_px<VT, OT, 2>(d, coords, cbs, cs, out, HW, B, st, upd); break;
+    case 3: launch_fwd_px<VT, OT, 3>(d, coords, cbs, cs, out, HW, B, st, upd); break;
+    default: launch_fwd_px<VT, OT, 4>(d, coords, cbs, cs, out, HW, B, st, upd); break;
   }
 }
 
@@ -1093,7 +784,8 @@ static int lookup_impl(const smoe_pyramid_t* pyr, const float* coords, int64_t c
     // which reads levels 0 and 2 and recomputes 1 and 3, can serve the lookup
     SMOE_REQUIRE((pyr->levels_missing & 0x5) == 0, SMOE_ERR_INVALID_ARG,
                  "lookup: an even level is marked missing (levels_missing=0x%x)", pyr->levels_missing);
-    SMOE_REQUIRE(radius == 4 && pyramid_vec_ok(pyr) && (g_fwd_kernel == 0 || g_fwd_kernel == 1 || g_fwd_kernel == 4),
+    SMOE_REQUIRE(radius == 4 && pyramid_vec_ok(pyr) &&
+                     (fwd_kernel_choice() == 0 || fwd_kernel_choice() == 1 || fwd_kernel_choice() == 4),
                  SMOE_ERR_INVALID_ARG,
                  "lookup: levels 0x%x of the pyramid were not built; radius %d / this kernel choice "
                  "needs them (build without SMOE_BUILD_SKIP_ODD_LEVELS)", pyr->levels_missing, radius);
@@ -1126,7 +818,9 @@ static int lookup_impl(const smoe_pyramid_t* pyr, const float* coords, int64_t c
 
 extern "C" {
 
+#ifdef SMOE_CROSSCHECK
 void smoe_corr_debug_set_lookup_kernel(int which) { smoe::g_fwd_kernel_tls = which; }
+#endif
 
 int smoe_corr_lookup(const smoe_pyramid_t* pyr, const float* coords, int64_t coords_batch_stride,
                      float coord_scale, int radius, void* out, int out_dtype,
@@ -1230,8 +924,11 @@ int smoe_corr_lookup_bwd_batched(const smoe_pyramid_t* g0, int num_levels, int n
   SMOE_REQUIRE(coords && coords_batch_stride && grad_out, SMOE_ERR_INVALID_ARG, "lookup_bwd_batched: NULL array");
   SMOE_REQUIRE(g0->B <= 65535, SMOE_ERR_UNSUPPORTED, "lookup_bwd_batched: batch %d > 65535", g0->B);
   const int ges = dtype_size(grad_out_dtype);
-  // SMOE_CORR_BWD_BATCHED=staged selects the first version (cp.async-staged tiles, 16-byte rules)
-  static const bool staged = [] { const char* e = getenv("SMOE_CORR_BWD_BATCHED"); return e && e[0] == 's'; }();
+#ifdef SMOE_CROSSCHECK
+  const bool staged = tuning().bwd_staged != 0;    // first version (cp.async-staged tiles, 16-byte rules)
+#else
+  constexpr bool staged = false;
+#endif
   SMOE_REQUIRE(!staged || (HW * ges) % 16 == 0, SMOE_ERR_UNSUPPORTED,
                "lookup_bwd_batched: H*W1=%lld planes are not 16-byte multiples (cp.async staging)", HW);
   BwdBatch batch;
@@ -1255,22 +952,35 @@ int smoe_corr_lookup_bwd_batched(const smoe_pyramid_t* g0, int num_levels, int n
     if (l < num_levels) off += (w + 3) / 4 * 4;
     w /= 2;
   }
-  // consecutive pixel rows must start 4 banks apart (rowlen % 32 == 4): the 8 pixels of a warp
-  // then cover all 32 banks.  (rowlen % 32 == 0, which W2=184 happened to give with a fixed pad,
-  // made every scatter an 8-way bank conflict: 810 us instead of ~200 us at config 2.)
-  geo.rowlen = off + ((4 - off % 32) + 32) % 32;
-  // warp-per-level kernel: lane = pixel, so consecutive lanes hit rows `rowlen` apart at columns
-  // that advance by 2^-level per pixel; rowlen % 32 == 2 makes level 0 conflict-free (3 banks per
-  // pixel) and keeps the coarser levels at <= 2-way
-  if (!staged) geo.rowlen = off + ((2 - off % 32) + 32) % 32;
-  const size_t smem = (size_t)kTilePx * geo.rowlen * 4 +
-                      (staged ? kBatchedStages * ((size_t)num_levels * 9 * (kTilePx + 32 / ges) * ges + kTilePx * 4) : 0);
+  // lane = pixel, so consecutive lanes hit rows `rowlen` apart at columns that advance by 2^-level
+  // per pixel; rowlen % 32 == 2 makes level 0 conflict-free for smooth disparities (3 banks per
+  // pixel) and keeps the coarser levels at <= 2-way.  (rowlen % 32 == 0, which W2=184 happened to
+  // give with a fixed pad, made every scatter an 8-way bank conflict.)
+  const int rowmod = kXcheck ? (tuning().bwd_rowmod & 31) : 2;
+  geo.rowlen = off + ((rowmod - off % 32) + 32) % 32;
+  size_t smem = (size_t)kTilePx * geo.rowlen * 4;
+#ifdef SMOE_CROSSCHECK
+  if (staged) {   // the staged kernel wants pixel rows 4 banks apart (the 8 pixels of a warp cover all banks)
+    geo.rowlen = off + ((4 - off % 32) + 32) % 32;
+    smem = (size_t)kTilePx * geo.rowlen * 4 +
+           kBatchedStages * ((size_t)num_levels * 9 * (kTilePx + 32 / ges) * ges + kTilePx * 4);
+  }
+#endif
   // (the Python side bounds this with off + 32 words per row)
   SMOE_REQUIRE(smem <= 227 * 1024, SMOE_ERR_UNSUPPORTED,
                "lookup_bwd_batched: W2=%d needs %zu bytes of shared memory per CTA", g0->width[0], smem);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   dim3 grid((unsigned)((HW + kTilePx - 1) / kTilePx), g0->B);
   float* out = static_cast<float*>(g0->level_ptr[0]);
+  const int ns = kXcheck ? tuning().bwd_split : kDefaultBwdSplit;
+#define SMOE_LAUNCH_LVL(GT, NLV, NSV)                                                                    \
+  do {                                                                                                   \
+    SMOE_CUDA_OK(cudaFuncSetAttribute(lookup_bwd_lvl_kernel<GT, NLV, NSV>,                               \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
+    SMOE_CUDA_OK(launch_kernel(lookup_bwd_lvl_kernel<GT, NLV, NSV>, grid, dim3(128 * NSV), smem, st,     \
+                               batch, geo, out, (long long)g0->pitch[0], (int)HW, accumulate));           \
+  } while (0)
+#ifdef SMOE_CROSSCHECK
 #define SMOE_LAUNCH_BATCHED(GT, NLV)                                                                     \
   do {                                                                                                   \
     if (staged) {                                                                                        \
@@ -1278,13 +988,18 @@ int smoe_corr_lookup_bwd_batched(const smoe_pyramid_t* g0, int num_levels, int n
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
       SMOE_CUDA_OK(launch_kernel(lookup_bwd_batched_kernel<GT, NLV>, grid, dim3(kBatchedThreads), smem,  \
                                  st, batch, geo, out, (long long)g0->pitch[0], (int)HW, accumulate));     \
+    } else if (ns == 1) {                                                                                \
+      SMOE_LAUNCH_LVL(GT, NLV, 1);                                                                       \
+    } else if (ns == 3) {                                                                                \
+      SMOE_LAUNCH_LVL(GT, NLV, 3);                                                                       \
     } else {                                                                                             \
-      SMOE_CUDA_OK(cudaFuncSetAttribute(lookup_bwd_lvl_kernel<GT, NLV>,                                  \
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
-      SMOE_CUDA_OK(launch_kernel(lookup_bwd_lvl_kernel<GT, NLV>, grid, dim3(128), smem, st, batch, geo,  \
-                                 out, (long long)g0->pitch[0], (int)HW, accumulate));                     \
+      SMOE_LAUNCH_LVL(GT, NLV, 2);                                                                       \
     }                                                                                                    \
   } while (0)
+#else
+#define SMOE_LAUNCH_BATCHED(GT, NLV) SMOE_LAUNCH_LVL(GT, NLV, kDefaultBwdSplit)
+  (void)ns;
+#endif
   const bool f16g = grad_out_dtype == SMOE_DTYPE_F16;
   switch (num_levels) {
     case 1: if (f16g) SMOE_LAUNCH_BATCHED(__half, 1); else SMOE_LAUNCH_BATCHED(float, 1); break;
@@ -1293,7 +1008,34 @@ int smoe_corr_lookup_bwd_batched(const smoe_pyramid_t* g0, int num_levels, int n
     default: if (f16g) SMOE_LAUNCH_BATCHED(__half, 4); else SMOE_LAUNCH_BATCHED(float, 4); break;
   }
 #undef SMOE_LAUNCH_BATCHED
+#undef SMOE_LAUNCH_LVL
   return check_launch("lookup backward (batched)");
+}
+
+int smoe_corr_fill_levels(const smoe_pyramid_t* pyr, smoe_stream_t stream) {
+  using namespace smoe;
+  if (int rc = validate_pyramid(pyr, "fill_levels")) return rc;
+  const int missing = pyr->levels_missing & ((1 << pyr->num_levels) - 1);
+  SMOE_REQUIRE((missing & 1) == 0, SMOE_ERR_INVALID_ARG, "fill_levels: level 0 cannot be recomputed");
+  const long long rows = (long long)pyr->B * pyr->H * pyr->W1;
+  if (rows == 0 || missing == 0) return SMOE_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int i = 1; i < pyr->num_levels; ++i) {
+    if (!((missing >> i) & 1) || pyr->width[i] == 0) continue;
+    SMOE_REQUIRE(pyr->width[i] <= pyr->width[i - 1] / 2, SMOE_ERR_INVALID_ARG,
+                 "fill_levels: level %d width %d > floor(%d/2)", i, pyr->width[i], pyr->width[i - 1]);
+    const long long total = rows * pyr->width[i];
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    if (pyr->dtype == SMOE_DTYPE_F16)
+      launch_kernel(fill_level_kernel<__half>, dim3(blocks), dim3(256), 0, st,
+                    static_cast<const __half*>(pyr->level_ptr[i - 1]), (long long)pyr->pitch[i - 1],
+                    static_cast<__half*>(pyr->level_ptr[i]), (long long)pyr->pitch[i], pyr->width[i], total);
+    else
+      launch_kernel(fill_level_kernel<float>, dim3(blocks), dim3(256), 0, st,
+                    static_cast<const float*>(pyr->level_ptr[i - 1]), (long long)pyr->pitch[i - 1],
+                    static_cast<float*>(pyr->level_ptr[i]), (long long)pyr->pitch[i], pyr->width[i], total);
+  }
+  return check_launch("fill_levels");
 }
 
 int smoe_corr_fold_pyramid_grad(const smoe_pyramid_t* gp, smoe_stream_t stream) {

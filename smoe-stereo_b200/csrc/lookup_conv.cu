@@ -11,7 +11,7 @@
 // (kind::tf32, fp32 accumulate in TMEM), and the epilogue reads TMEM with lane == pixel: for a
 // fixed output channel the 32 lanes of a warp hold 32 consecutive pixels, i.e. one 128-byte line
 // of the channel-major output -- the accumulator layout does the transpose.
-#include <stdlib.h>
+#include <type_traits>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -50,156 +50,9 @@ __device__ __forceinline__ void tmem_ld_32x32_x16(uint32_t taddr, uint32_t (&r)[
 // VT: pyramid element type; LT: the type the unfused lookup would return (float for CorrBlock1D,
 // the volume dtype for CorrBlockFast1D -- its interpolation arithmetic is reproduced);
 // CT: output type of the convolution.
-template <typename VT, typename LT, typename CT, int NL, bool STREAM>
-__global__ void __launch_bounds__(kFcThreads)
-lookup_conv_kernel(PyrDev pyr, const float* __restrict__ coords, long long coords_bstride,
-                   float coord_scale, const float* __restrict__ weight, const float* __restrict__ bias,
-                   int cout, int relu, uint32_t tmem_cols, CT* __restrict__ out, int HW, CoordUpd upd) {
-  constexpr int R = 4;
-  constexpr int RD = 2 * R + 1;
-  constexpr int K = NL * RD;                          // input channels of the convolution
-  constexpr int KMMA = (K + 7) / 8 * 8;               // K covered by the MMAs (zero padded)
-  constexpr int EPL = Vec16<VT>::N;
-  constexpr int LOG_EPL = (EPL == 4) ? 2 : 3;
-  constexpr int QMAX = (EPL - 1 + 2 * R + 1) >> LOG_EPL;
-  static_assert(KMMA <= kFcKPad, "K must fit the padded operand");
-
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t s_bar;
-  __shared__ uint32_t s_tmem;
-  __shared__ float s_bias[kFcMaxCout];
-  const uint32_t sA = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;    // swizzle atoms: 1 KiB aligned
-  const uint32_t sB = sA + kFcABytes;
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int p = tid >> 2, q = tid & 3;
-  const int b = blockIdx.y;
-  const int hw0 = blockIdx.x * kFcPx;
-  const int hw = hw0 + p;
-  const bool valid = hw < HW;
-
-  if (warp == 0) {      // (allocating after the gathers are issued measured slower: 9.8 vs 8.8 us)
-    ptx::tmem_alloc(ptx::smem_u32(&s_tmem), tmem_cols);
-    ptx::tmem_relinquish();
-  }
-  if (tid == 32) {
-    ptx::mbar_init(ptx::smem_u32(&s_bar), 1);
-    ptx::fence_barrier_init();
-  }
-  pdl_wait();
-  // ---- gather: issue the window loads of all levels first
-  const float x0 = valid ? fetch_coord(coords, coords_bstride, upd, b, hw, q == 0) * coord_scale : 0.f;
-  const long long row = (long long)b * HW + hw;
-  float v[NL][EPL];
-  float dxs[NL];
-  int shift[NL];
-  float lscale = 1.0f;
-#pragma unroll
-  for (int l = 0; l < NL; ++l) {
-    int base;
-    split_coord(x0 * lscale, R, base, dxs[l]);
-    lscale *= 0.5f;
-    const int s = base & (EPL - 1);
-    const int ci = (base >> LOG_EPL) + q;
-    shift[l] = s;
-    const int width = pyr.width[l];
-    const unsigned nchunks = (unsigned)(width + EPL - 1) >> LOG_EPL;
-    const bool need = valid && (q < QMAX || (q == QMAX && s + 2 * R + 1 >= QMAX * EPL)) &&
-                      (unsigned)ci < nchunks;
-#pragma unroll
-    for (int j = 0; j < EPL; ++j) v[l][j] = 0.f;
-    if (need) {
-      const VT* src = static_cast<const VT*>(pyr.ptr[l]) + row * pyr.pitch[l] + (long long)ci * EPL;
-      Vec16<VT>::template load<STREAM>(src, v[l]);
-      if (__builtin_expect((ci + 1) * EPL > width, 0)) {
-#pragma unroll
-        for (int j = 0; j < EPL; ++j)
-          if (ci * EPL + j >= width) v[l][j] = 0.f;
-      }
-    }
-  }
-  // ---- weights -> B operand (tf32, zero padded to 64 columns) while the gathers are in flight
-  for (int idx = tid; idx < cout * (kFcKPad / 4); idx += kFcThreads) {
-    const int n = idx / (kFcKPad / 4), piece = idx % (kFcKPad / 4);
-    uint32_t w[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int k = piece * 4 + j;
-      w[j] = k < K ? to_tf32(__ldg(weight + (long long)n * K + k)) : 0u;
-    }
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sB + kmajor_off(n, piece * 4, cout)),
-                 "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
-                 : "memory");
-  }
-  if (tid < cout) s_bias[tid] = bias != nullptr ? __ldg(bias + tid) : 0.f;
-  // zero the K padding the MMAs read (columns K .. KMMA-1 of every pixel row)
-  if (q == 0) {
-#pragma unroll
-    for (int k = K; k < KMMA; ++k)
-      asm volatile("st.shared.b32 [%0], %1;" ::"r"(sA + kmajor_off(p, k, kFcPx)), "r"(0u) : "memory");
-  }
-  // ---- interpolate; tap k of level l sits at window position shift+k of the 4-chunk span
-#pragma unroll
-  for (int l = 0; l < NL; ++l) {
-    const float nxt = __shfl_down_sync(0xffffffffu, v[l][0], 1);
-    float e[EPL];
-    LerpChunk<LT, EPL>::run(v[l], nxt, dxs[l], e);
-#pragma unroll
-    for (int i = 0; i < EPL; ++i) {
-      const int k = q * EPL + i - shift[l];
-      if (k >= 0 && k < RD)
-        asm volatile("st.shared.b32 [%0], %1;" ::"r"(sA + kmajor_off(p, l * RD + k, kFcPx)),
-                     "r"(to_tf32(e[i]))
-                     : "memory");
-    }
-  }
-  pdl_launch_dependents();
-  ptx::fence_proxy_async_smem();          // generic-proxy operand writes -> tensor-core (async) proxy
-  ptx::tc_fence_before_sync();
-  __syncthreads();
-  ptx::tc_fence_after_sync();
-  const uint32_t tmem = s_tmem;
-  if (tid == 0) {
-    // c_format f32 | tf32 x tf32 | A, B K-major | N | M
-    const uint32_t idesc = (1u << 4) | (ptx::kFmtTF32 << 7) | (ptx::kFmtTF32 << 10) |
-                           (((uint32_t)cout >> 3) << 17) | ((uint32_t)(kFcPx >> 4) << 24);
-#pragma unroll
-    for (int ks = 0; ks < KMMA / 8; ++ks) {
-      const int atom = (ks * 8) >> 5, kin = (ks * 8) & 31;
-      // K-major SW128: 8-row groups 1 KiB apart (SBO), 32 bytes per UMMA_K inside the 128-byte row
-      const uint64_t adesc = ptx::make_smem_desc(sA + atom * kFcPx * 128 + kin * 4, 16, 1024, ptx::kLayoutSwizzle128B);
-      const uint64_t bdesc = ptx::make_smem_desc(sB + atom * cout * 128 + kin * 4, 16, 1024, ptx::kLayoutSwizzle128B);
-      ptx::mma_tf32(tmem, adesc, bdesc, idesc, ks != 0 ? 1u : 0u);
-    }
-    ptx::tc_commit(ptx::smem_u32(&s_bar));
-  }
-  ptx::mbar_wait(ptx::smem_u32(&s_bar), 0);
-  ptx::tc_fence_after_sync();
-  // ---- epilogue: TMEM lane == pixel; the 4 warps of a lane quadrant split the output channels
-  const int quad = warp & 3, part = warp >> 2;
-  const int px = quad * 32 + lane;
-  const bool store = hw0 + px < HW;
-  CT* obase = out + (long long)b * cout * HW + hw0 + px;
-  for (int c0 = part * 16; c0 < cout; c0 += 64) {
-    uint32_t acc[16];
-    tmem_ld_32x32_x16(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, acc);
-    ptx::tmem_ld_wait();
-    if (store) {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float r = __uint_as_float(acc[j]) + s_bias[c0 + j];
-        if (relu) r = fmaxf(r, 0.f);
-        obase[(long long)(c0 + j) * HW] = from_float<CT>(r);
-      }
-    }
-  }
-  ptx::tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 0) {
-    ptx::tc_fence_after_sync();
-    ptx::tmem_dealloc(tmem, tmem_cols);
-  }
-}
+#ifdef SMOE_CROSSCHECK
+#include "xcheck_lookup_conv.cuh"     // first version (4 lanes per pixel), cross-check library only
+#endif
 
 // Second version: thread = pixel (PxPair gather, px_gather.cuh).  128 threads per CTA: each thread
 // gathers its pixel's two segments (12 independent 16-byte loads), stages its share of the weights
@@ -207,12 +60,16 @@ lookup_conv_kernel(PyrDev pyr, const float* __restrict__ coords, long long coord
 // K-major SWIZZLE_128B tile), one thread issues the MMAs, and the same thread then reads its own
 // TMEM lane (lane == pixel) for the epilogue.  A quarter of the threads and ~3x fewer instructions
 // than the lane-group version, four CTAs per SM instead of two.
-template <typename VT, typename LT, typename CT, int NL, bool STREAM>
+// LD256: fp32 volumes beyond L2 fetch their segments with 256-bit loads (PxPair256), level-0 fills
+// evict_first, like the plain lookup.
+template <typename VT, typename LT, typename CT, int NL, bool STREAM, bool LD256 = false>
 __global__ void __launch_bounds__(kFcPx)
 lookup_conv_px_kernel(PyrDev pyr, const float* __restrict__ coords, long long coords_bstride,
                       float coord_scale, const float* __restrict__ weight, const float* __restrict__ bias,
                       int cout, int relu, uint32_t tmem_cols, CT* __restrict__ out, int HW, CoordUpd upd) {
-  using Pair = PxPair<VT, STREAM>;
+  static_assert(!LD256 || (sizeof(VT) == 4 && STREAM), "256-bit segment loads: streaming fp32 volumes");
+  using Pair = typename std::conditional<LD256, PxPair256<STREAM>, PxPair<VT, STREAM>>::type;
+  using ET = typename std::conditional<LD256, float, VT>::type;
   constexpr int RD = Pair::RD;
   constexpr int NP = (NL + 1) / 2;
   constexpr int K = NL * RD;                          // input channels of the convolution
@@ -251,8 +108,8 @@ lookup_conv_px_kernel(PyrDev pyr, const float* __restrict__ coords, long long co
     const VT* fine_row = static_cast<const VT*>(i == 0 ? pyr.ptr[0] : pyr.ptr[2]) +
                          row * (i == 0 ? pyr.pitch[0] : pyr.pitch[2]);
     // an invalid (tail) pixel gathers with a non-finite coordinate: every load is skipped
-    pair[i].load(fine_row, i == 0 ? pyr.width[0] : pyr.width[2],
-                 valid ? x0 * (i == 0 ? 1.0f : 0.25f) : __int_as_float(0x7fc00000));
+    pair[i].load(reinterpret_cast<const ET*>(fine_row), i == 0 ? pyr.width[0] : pyr.width[2],
+                 valid ? x0 * (i == 0 ? 1.0f : 0.25f) : __int_as_float(0x7fc00000), i == 0 ? 1 : 0);
   }
   // ---- weights -> B operand (tf32, zero padded) while the gathers are in flight.  Row n of the
   // weights is K contiguous floats; thread (n = idx / KP4, piece) handles one 16-byte piece.  All
@@ -356,6 +213,7 @@ lookup_conv_px_kernel(PyrDev pyr, const float* __restrict__ coords, long long co
 }
 
 bool pyramid_vec_ok(const smoe_pyramid_t* p);   // lookup.cu
+bool pyramid_ld256_ok(const PyrDev& d, int NL);   // lookup.cu
 
 template <typename VT, typename LT, typename CT>
 static int launch_lookup_conv(const smoe_pyramid_t* pyr, const float* coords, long long cbs, float cs,
@@ -368,31 +226,46 @@ static int launch_lookup_conv(const smoe_pyramid_t* pyr, const float* coords, lo
   while ((int)cols < cout) cols <<= 1;
   const bool big = (long long)pyr->B * HW * d.pitch[0] * (long long)sizeof(VT) > (96ll << 20);
   dim3 grid((HW + kFcPx - 1) / kFcPx, pyr->B);
-  // SMOE_CORR_LOOKUP_CONV=lanes|px forces one version.  Default: thread-per-pixel (cfg1 8.98 -> 6.35 us,
-  // fp16 volumes 10.7 -> 6.4 us and 72 -> 57 us at B=8 96x312), except fp32 volumes beyond L2, where
-  // the lane-group version still measures ~15% faster (66 vs 78 us): both are latency-bound there
-  // (4 CTAs per SM, serial gather -> MMA -> epilogue chain; profiles/r01/README.md).
-  static const int forced = [] {
-    const char* e = getenv("SMOE_CORR_LOOKUP_CONV");
-    return !e ? 0 : (e[0] == 'l' ? 1 : 2);
-  }();
+  // Thread-per-pixel kernel everywhere (cfg1 8.98 -> 6.35 us vs the lane-group version, fp16
+  // volumes 10.7 -> 6.4 us and 72 -> 57 us at B=8 96x312); fp32 volumes beyond L2 use its 256-bit
+  // gather.  The lane-group version lives in the cross-check library (SMOE_CORR_LOOKUP_CONV=lanes).
   const bool missing = (pyr->levels_missing & ((1 << pyr->num_levels) - 1)) != 0;   // odd levels not built
-  SMOE_REQUIRE(!(missing && forced == 1) && (pyr->levels_missing & 0x5) == 0, SMOE_ERR_INVALID_ARG,
+  SMOE_REQUIRE((pyr->levels_missing & 0x5) == 0, SMOE_ERR_INVALID_ARG,
                "lookup_conv1x1: levels 0x%x of the pyramid were not built", pyr->levels_missing);
-  const bool lanes = !missing && (forced == 1 || (forced == 0 && big && sizeof(VT) == 4));
+#ifdef SMOE_CROSSCHECK
+  const bool lanes = tuning().conv_lanes != 0;
+  SMOE_REQUIRE(!(missing && lanes), SMOE_ERR_INVALID_ARG,
+               "lookup_conv1x1: the lane-group kernel needs all levels (levels_missing=0x%x)", pyr->levels_missing);
+#else
+  (void)missing;
+#endif
+  const bool ld256 = big && sizeof(VT) == 4 && pyramid_ld256_ok(d, pyr->num_levels) && tuning().px_ld256 != 0;
+#define SMOE_FC_PX(NLV, STREAMV, LD)                                                              \
+  do {                                                                                            \
+    auto kern = lookup_conv_px_kernel<VT, LT, CT, NLV, STREAMV, LD>;                              \
+    SMOE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    SMOE_CUDA_OK(launch_kernel_pdl(kern, grid, dim3(kFcPx), smem, st, d, coords, cbs, cs, weight, \
+                                   bias, cout, relu, cols, static_cast<CT*>(out), HW, upd));      \
+  } while (0)
+#ifdef SMOE_CROSSCHECK
+#define SMOE_FC_LANES(NLV, STREAMV)                                                               \
+  if (lanes) {                                                                                    \
+    auto kern = lookup_conv_kernel<VT, LT, CT, NLV, STREAMV>;                                     \
+    SMOE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    SMOE_CUDA_OK(launch_kernel(kern, grid, dim3(kFcThreads), smem, st, d, coords, cbs, cs, weight, \
+                               bias, cout, relu, cols, static_cast<CT*>(out), HW, upd));          \
+    break;                                                                                        \
+  }
+#else
+#define SMOE_FC_LANES(NLV, STREAMV)
+#endif
 #define SMOE_FC_LAUNCH(NLV, STREAMV)                                                              \
   do {                                                                                            \
-    if (lanes) {                                                                                  \
-      auto kern = lookup_conv_kernel<VT, LT, CT, NLV, STREAMV>;                                   \
-      SMOE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      SMOE_CUDA_OK(launch_kernel(kern, grid, dim3(kFcThreads), smem, st, d, coords, cbs, cs, weight, \
-                                 bias, cout, relu, cols, static_cast<CT*>(out), HW, upd));        \
-    } else {                                                                                      \
-      auto kern = lookup_conv_px_kernel<VT, LT, CT, NLV, STREAMV>;                                \
-      SMOE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      SMOE_CUDA_OK(launch_kernel_pdl(kern, grid, dim3(kFcPx), smem, st, d, coords, cbs, cs, weight, \
-                                     bias, cout, relu, cols, static_cast<CT*>(out), HW, upd));    \
+    SMOE_FC_LANES(NLV, STREAMV)                                                                   \
+    if constexpr (STREAMV && sizeof(VT) == 4) {                                                   \
+      if (ld256) { SMOE_FC_PX(NLV, true, true); break; }                                          \
     }                                                                                             \
+    SMOE_FC_PX(NLV, STREAMV, false);                                                              \
   } while (0)
 #define SMOE_FC_LEVELS(STREAMV)                                                                   \
   switch (pyr->num_levels) {                                                                      \
@@ -404,6 +277,8 @@ static int launch_lookup_conv(const smoe_pyramid_t* pyr, const float* coords, lo
   if (big) { SMOE_FC_LEVELS(true) } else { SMOE_FC_LEVELS(false) }
 #undef SMOE_FC_LEVELS
 #undef SMOE_FC_LAUNCH
+#undef SMOE_FC_LANES
+#undef SMOE_FC_PX
   return check_launch("lookup_conv_kernel");
 }
 

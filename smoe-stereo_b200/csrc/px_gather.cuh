@@ -40,7 +40,7 @@ struct PxPair {
   int cs;       // first chunk of the segment
 
   // xl: the pixel's x coordinate in the FINE level of the pair; `fine` points at that level's row
-  __device__ __forceinline__ void load(const VT* __restrict__ fine_row, int width, float xl) {
+  __device__ __forceinline__ void load(const VT* __restrict__ fine_row, int width, float xl, int /*hint*/ = 0) {
     int basef, basec;
     split_coord(xl, R, basef, dxf);
     split_coord(xl * 0.5f, R, basec, dxc);
@@ -120,18 +120,31 @@ struct PxPair256 {
   int odd;      // basef - S - R: 0 or 1 (-1: parked coordinate, everything is zero)
   int i0;       // fine index of v[0] (may be negative)
 
-  __device__ __forceinline__ static void load32(const float* p, float (&t)[8]) {
-    if (STREAM)
-      asm volatile("ld.global.L1::no_allocate.L2::64B.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                   : "=f"(t[0]), "=f"(t[1]), "=f"(t[2]), "=f"(t[3]), "=f"(t[4]), "=f"(t[5]), "=f"(t[6]), "=f"(t[7])
-                   : "l"(p));
-    else
+  // hint (STREAM only): L2 eviction priority of the fill -- 0 normal, 1 evict_first (single-use level-0
+  // segments of a volume that streams from DRAM), 2 evict_last (the 16x smaller level 2, which can stay
+  // L2-resident across the iterations of a GRU loop).  SASS: LDG.E.NA.{EN,EF,EL}L2.LTC64B.256.
+  __device__ __forceinline__ static void load32(const float* p, float (&t)[8], int hint) {
+    if (STREAM) {
+      if (hint == 1)
+        asm volatile("ld.global.L1::no_allocate.L2::evict_first.L2::64B.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(t[0]), "=f"(t[1]), "=f"(t[2]), "=f"(t[3]), "=f"(t[4]), "=f"(t[5]), "=f"(t[6]), "=f"(t[7])
+                     : "l"(p));
+      else if (hint == 2)
+        asm volatile("ld.global.L1::no_allocate.L2::evict_last.L2::64B.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(t[0]), "=f"(t[1]), "=f"(t[2]), "=f"(t[3]), "=f"(t[4]), "=f"(t[5]), "=f"(t[6]), "=f"(t[7])
+                     : "l"(p));
+      else
+        asm volatile("ld.global.L1::no_allocate.L2::64B.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(t[0]), "=f"(t[1]), "=f"(t[2]), "=f"(t[3]), "=f"(t[4]), "=f"(t[5]), "=f"(t[6]), "=f"(t[7])
+                     : "l"(p));
+    } else {
       asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                    : "=f"(t[0]), "=f"(t[1]), "=f"(t[2]), "=f"(t[3]), "=f"(t[4]), "=f"(t[5]), "=f"(t[6]), "=f"(t[7])
                    : "l"(p));
+    }
   }
 
-  __device__ __forceinline__ void load(const float* __restrict__ fine_row, int width, float xl) {
+  __device__ __forceinline__ void load(const float* __restrict__ fine_row, int width, float xl, int hint = 0) {
     int basef, basec;
     split_coord(xl, R, basef, dxf);
     split_coord(xl * 0.5f, R, basec, dxc);
@@ -151,7 +164,7 @@ struct PxPair256 {
       for (int e = 0; e < 8; ++e) t[e] = 0.f;
       // the last chunk is only needed when the segment starts 6 floats into the first one
       const bool need = odd >= 0 && (j < NCH - 1 || sh + SEG > 8 * (NCH - 1)) && ij + 8 > 0 && ij < width;
-      if (need) load32(src + 8 * j, t);
+      if (need) load32(src + 8 * j, t, hint);
 #pragma unroll
       for (int e = 0; e < 8; ++e) v[8 * j + e] = t[e];
     }

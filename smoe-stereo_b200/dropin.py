@@ -18,6 +18,7 @@ from . import corr_sampler as _sampler
 _NAMES = ("CorrBlock1D", "CorrBlockFast1D", "PytorchAlternateCorrBlock1D", "CorrSampler")
 _TARGETS = ("core.corr", "core.raft_stereo", "core.SMoEStereo")
 _saved: dict = {}
+_ABSENT = object()
 
 
 def install(modules=_TARGETS) -> list[str]:
@@ -36,8 +37,11 @@ def install(modules=_TARGETS) -> list[str]:
                 _saved[(mname, n)] = getattr(mod, n)
                 setattr(mod, n, getattr(_corr, n))
                 replaced.append(f"{mname}.{n}")
-        if hasattr(mod, "corr_sampler") and mod.corr_sampler is not _sampler:
-            _saved[(mname, "corr_sampler")] = mod.corr_sampler
+        # core/corr.py:5-8 binds `corr_sampler` inside try/except: the global is absent when the
+        # reference extension was never compiled; the reference's own CorrSampler needs it either way
+        if (hasattr(mod, "corr_sampler") or mname == "core.corr") and \
+                getattr(mod, "corr_sampler", None) is not _sampler:
+            _saved[(mname, "corr_sampler")] = getattr(mod, "corr_sampler", _ABSENT)
             mod.corr_sampler = _sampler
             replaced.append(f"{mname}.corr_sampler")
     return replaced
@@ -51,5 +55,9 @@ def uninstall() -> None:
             else:
                 sys.modules[n] = old
         elif mname in sys.modules:
-            setattr(sys.modules[mname], n, old)
+            if old is _ABSENT:
+                if hasattr(sys.modules[mname], n):
+                    delattr(sys.modules[mname], n)
+            else:
+                setattr(sys.modules[mname], n, old)
         del _saved[(mname, n)]

@@ -38,3 +38,48 @@ def make_coords(B, H, W1, W2, T, seed, oob_frac=0.02):
         out[t, :, 0] = x.astype(np.float32)
         out[t, :, 1] = ys
     return out
+
+
+XCHECK_LIB = __import__("os").path.join(__import__("os").path.dirname(__import__("os").path.abspath(__file__)),
+                                        "_build", "libsmoecorr_xcheck.so")
+
+
+class xcheck_lib:
+    """Context manager: run the package on the CROSS-CHECK library (tests/_build/libsmoecorr_xcheck.so:
+    the product kernels plus the superseded ones and the debug selectors, csrc/xcheck_api.h) instead
+    of libsmoecorr.so.  `with xcheck_lib(bwd_staged=1) as L:` also sets Tuning fields for the block."""
+
+    def __init__(self, **tuning):
+        self.tuning = tuning
+        self.saved = {}
+
+    def __enter__(self):
+        import ctypes
+        import os
+        import pytest
+        from smoe_stereo_b200 import _lib, corr
+        if not os.path.exists(XCHECK_LIB):
+            pytest.skip("tests/_build/libsmoecorr_xcheck.so not built (python smoe-stereo_b200/build.py --xcheck)")
+        L = ctypes.CDLL(XCHECK_LIB)
+        missing = [s for s in _lib.SYMBOLS + _lib.XCHECK_SYMBOLS if not hasattr(L, s)]
+        assert not missing, missing
+        _lib._declare(L)
+        self.L, self.old = L, _lib._lib
+        _lib._lib = L
+        _lib._fast = None
+        corr._lookup_fn = None
+        for k, v in self.tuning.items():
+            assert L.smoe_corr_debug_set_tuning(k.encode(), int(v)) == 0, k
+        return L
+
+    def __exit__(self, *exc):
+        from smoe_stereo_b200 import _lib, corr
+        defaults = dict(pdl=2, fwd_kernel=0, px_tpb=32, px_split=1, px_ld256=-1, px_hint=1, lookup_tile=32,
+                        bwd_staged=0, bwd_split=2, bwd_rowmod=2, build_pair=0, build_stages=0, build_debug=0,
+                        conv_lanes=0)
+        for k in self.tuning:
+            self.L.smoe_corr_debug_set_tuning(k.encode(), defaults[k])
+        self.L.smoe_corr_debug_set_lookup_kernel(-1)
+        _lib._lib = self.old
+        _lib._fast = None
+        corr._lookup_fn = None

@@ -106,14 +106,10 @@ def test_unbuilt_levels_and_layout_flags_are_validated_without_a_gpu(built):
     p = _fake_pyramid(built, missing=0b0100)
     rc = L.smoe_corr_lookup(ctypes.byref(p), fake, 16, 1.0, 4, fake, built.DTYPE_F32, None)
     assert rc == built.ERR_INVALID_ARG and "even level" in built.last_error()
-    # forcing a lane-group kernel on such a pyramid is refused as well
-    p = _fake_pyramid(built, missing=0b1010)
-    L.smoe_corr_debug_set_lookup_kernel(3)
-    try:
-        rc = L.smoe_corr_lookup(ctypes.byref(p), fake, 16, 1.0, 4, fake, built.DTYPE_F32, None)
-    finally:
-        L.smoe_corr_debug_set_lookup_kernel(-1)
-    assert rc == built.ERR_INVALID_ARG and "were not built" in built.last_error()
+    # smoe_corr_fill_levels cannot recompute level 0
+    p = _fake_pyramid(built, missing=0b0001)
+    rc = L.smoe_corr_fill_levels(ctypes.byref(p), None)
+    assert rc == built.ERR_INVALID_ARG and "level 0" in built.last_error()
     # channels-last needs C*sizeof(T) % 16 == 0
     p = _fake_pyramid(built, W2=40)
     p.H, p.W1 = 3, 40

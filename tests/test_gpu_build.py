@@ -173,19 +173,19 @@ def test_middlebury_full_resolution_single_gpu(sb, oracle):
     (1, 64, 4, 37, 50),         # odd widths -> pitch-padded operands, partial tiles everywhere
 ])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
-def test_build_cta_pair_kernel_is_bit_identical(sb, monkeypatch, shape, dtype):
-    """The opt-in CTA-pair kernel (tcgen05 cta_group::2, SMOE_CORR_BUILD_PAIR=1) accumulates the
-    same products in the same order as the one-CTA kernel: every level must match bit for bit."""
-    from gpu_util import dev
+def test_build_cta_pair_kernel_is_bit_identical(sb, shape, dtype):
+    """The CTA-pair kernel (tcgen05 cta_group::2; cross-check library only, Tuning::build_pair)
+    accumulates the same products in the same order as the product's one-CTA kernel: every level
+    must match bit for bit."""
+    from gpu_util import dev, xcheck_lib
     B, C, H, W1, W2 = shape
     g = torch.Generator().manual_seed(11)
     f1 = torch.randn(B, C, H, W1, generator=g).to(dev(), dtype)
     f2 = torch.randn(B, C, H, W2, generator=g).to(dev(), dtype)
     cls = sb.CorrBlock1D if dtype == torch.float32 else sb.CorrBlockFast1D
-    monkeypatch.delenv("SMOE_CORR_BUILD_PAIR", raising=False)
     ref = [lv.clone() for lv in cls(f1, f2, num_levels=4, radius=4).corr_pyramid]
-    monkeypatch.setenv("SMOE_CORR_BUILD_PAIR", "1")
-    got = cls(f1, f2, num_levels=4, radius=4).corr_pyramid
+    with xcheck_lib(build_pair=1):
+        got = [lv.clone() for lv in cls(f1, f2, num_levels=4, radius=4).corr_pyramid]
     for i, (a, b) in enumerate(zip(ref, got)):
         assert torch.equal(a, b), f"level {i} differs"
 

@@ -140,9 +140,7 @@ def test_thread_per_pixel_kernel_equals_lane_group_kernels_bitwise(sb, dtype, le
     """lookup_fwd_px_kernel (one thread per pixel, register shift network) against the four-window
     and level-pair lane-group kernels on the same pyramid: bit for bit, including out-of-range,
     integer and non-finite coordinates, odd widths at every level and rows shorter than a segment."""
-    from gpu_util import dev, make_coords
-    from smoe_stereo_b200 import _lib
-    L = _lib.lib()
+    from gpu_util import dev, make_coords, xcheck_lib
     for (B, C, H, W1, W2) in [(2, 32, 9, 77, 77), (1, 16, 5, 40, 312), (1, 16, 3, 33, 22), (2, 16, 4, 50, 9)]:
         g = torch.Generator(device="cpu").manual_seed(W2)
         f1 = torch.randn(B, C, H, W1, generator=g).to(dev()).to(dtype)
@@ -156,31 +154,27 @@ def test_thread_per_pixel_kernel_equals_lane_group_kernels_bitwise(sb, dtype, le
         finally:
             corr_mod._skip_odd_levels = old_skip
         coords = torch.from_numpy(make_coords(B, H, W1, W2, 3, seed=W1)).to(dev())
-        if levels > 1:
-            # the block's build skipped levels 1/3: the lane-group kernels must refuse such a pyramid
-            L.smoe_corr_debug_set_lookup_kernel(3)
-            try:
-                with pytest.raises(RuntimeError, match="were not built"):
-                    blk(coords[0])
-            finally:
-                L.smoe_corr_debug_set_lookup_kernel(-1)
-            px_first = blk(coords[0]).clone()        # px on the two-level pyramid ...
-            blk._state.pyr.materialize()             # ... == px / vec / pair on the completed one
-            assert torch.equal(blk(coords[0]), px_first)
         coords[0, 0, 0, 0, :6] = torch.tensor([float("nan"), float("inf"), -float("inf"), 3e9, -0.0, W2 - 1.0])
         coords[1, 0, 0, 1, :4] = torch.tensor([-4.0, -4.5, W2 + 3.999, W2 + 4.0])
+        product = [blk(coords[t]).clone() for t in range(3)]      # libsmoecorr.so, levels 1/3 never written
         outs = {}
-        try:
+        with xcheck_lib() as L:
+            if levels > 1:
+                # the block's build skipped levels 1/3: the lane-group kernels must refuse such a pyramid
+                L.smoe_corr_debug_set_lookup_kernel(3)
+                with pytest.raises(RuntimeError, match="were not built"):
+                    blk(coords[0])
+                L.smoe_corr_debug_set_lookup_kernel(-1)
+            blk._state.pyr.materialize()             # complete the pyramid for the lane-group kernels
             for which, name in ((1, "px"), (2, "pair"), (3, "vec"), (4, "px256")):
                 L.smoe_corr_debug_set_lookup_kernel(which)
                 outs[name] = [blk(coords[t]).clone() for t in range(3)]
-        finally:
-            L.smoe_corr_debug_set_lookup_kernel(-1)
         for t in range(3):
-            assert torch.equal(outs["px"][t], outs["vec"][t]), (B, C, H, W1, W2, t)
+            assert torch.equal(product[t], outs["vec"][t]), (B, C, H, W1, W2, t)   # product == first design
+            assert torch.equal(outs["px"][t], outs["vec"][t])
             assert torch.equal(outs["pair"][t], outs["vec"][t])     # (pair falls through to vec for 1/3 levels)
             assert torch.equal(outs["px256"][t], outs["vec"][t])    # 256-bit loads (fp32 volumes; else == px)
-            assert torch.isfinite(outs["px"][t]).all()
+            assert torch.isfinite(product[t]).all()
 
 
 def test_kitti_cfg3_full_size_streaming_lookup_vs_oracle(sb, oracle):

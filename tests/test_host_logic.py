@@ -71,3 +71,38 @@ def test_shard_bounds():
     t = torch.arange(2 * 3 * 5 * 4).view(2, 3, 5, 4)
     assert torch.equal(sharding.take_shard(t, "rows", 2, 1), t[:, :, 3:])
     assert torch.equal(sharding.take_shard(t, "batch", 2, 0), t[:1])
+
+
+def _ref_models():
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    from baseline import ref_models
+    return ref_models
+
+
+@pytest.mark.skipif(not _ref_models().available(), reason="baseline/_ref/core not installed (tools/install_ref.sh)")
+def test_install_rebinds_every_reference_binding():
+    """All eight names the reference binds by value point at this package after
+    install(), and are restored by uninstall()."""
+    import smoe_stereo_b200 as sb
+    import sys
+    R = _ref_models()
+    R.import_core(with_ref_sampler=False)
+    import core.corr as c
+    import core.raft_stereo as rs
+    import core.SMoEStereo as ss
+    sb.uninstall()
+    stock = c.CorrBlock1D
+    sb.install()
+    try:
+        for mod in (c, rs, ss):
+            for n in ("CorrBlock1D", "CorrBlockFast1D", "PytorchAlternateCorrBlock1D"):
+                assert getattr(mod, n) is getattr(sb, n), (mod.__name__, n)
+        assert c.CorrSampler is sb.CorrSampler
+        assert sys.modules["corr_sampler"] is sb.corr_sampler and c.corr_sampler is sb.corr_sampler
+    finally:
+        sb.uninstall()
+    assert c.CorrBlock1D is stock and rs.CorrBlock1D is stock
