@@ -36,7 +36,7 @@ static Tuning read_tuning() {
   t.px_hint = env_int("SMOE_CORR_PX_HINT", t.px_hint);
   t.lookup_tile = env_int("SMOE_CORR_LOOKUP_TILE", t.lookup_tile);
   if (const char* e = getenv("SMOE_CORR_BWD_BATCHED")) t.bwd_staged = e[0] == 's';
-  t.bwd_split = env_int("SMOE_CORR_BWD_SPLIT", t.bwd_split);
+  t.bwd_kernel = env_int("SMOE_CORR_BWD_KERNEL", t.bwd_kernel);
   t.bwd_rowmod = env_int("SMOE_CORR_BWD_ROWMOD", t.bwd_rowmod);
   t.build_pair = env_int("SMOE_CORR_BUILD_PAIR", 0);
   t.build_stages = env_int("SMOE_CORR_BUILD_STAGES", 0);
@@ -87,7 +87,7 @@ int smoe_corr_debug_set_tuning(const char* name, int value) {
   using smoe::g_tuning;
 #define SMOE_FIELD(f) if (strcmp(name, #f) == 0) { g_tuning.f = value; return 0; }
   SMOE_FIELD(pdl) SMOE_FIELD(fwd_kernel) SMOE_FIELD(px_tpb) SMOE_FIELD(px_split) SMOE_FIELD(px_ld256)
-  SMOE_FIELD(px_hint) SMOE_FIELD(lookup_tile) SMOE_FIELD(bwd_staged) SMOE_FIELD(bwd_split)
+  SMOE_FIELD(px_hint) SMOE_FIELD(lookup_tile) SMOE_FIELD(bwd_staged) SMOE_FIELD(bwd_kernel)
   SMOE_FIELD(bwd_rowmod) SMOE_FIELD(build_pair) SMOE_FIELD(build_stages) SMOE_FIELD(build_debug)
   SMOE_FIELD(conv_lanes)
 #undef SMOE_FIELD

@@ -59,10 +59,10 @@ struct Tuning {
   int px_tpb = 32;         // pixels per CTA of the thread-per-pixel lookup
   int px_split = 1;        // one thread per level pair
   int px_ld256 = -1;       // 256-bit segment loads: -1 = for fp32 volumes beyond L2, 0 never, 1 always
-  int px_hint = 1;         // L2 eviction priorities of the streaming lookup (lookup.cu, PxHint)
+  int px_hint = -1;        // L2 eviction priorities of the streaming lookup (lookup.cu): -1 = by volume size
   int lookup_tile = 32;    // lane-group kernels: pixels per CTA
   int bwd_staged = 0;      // first version of the batched backward (cross-check build only)
-  int bwd_split = 2;       // threads per (pixel, level) in lookup_bwd_lvl_kernel: 1, 2 or 3
+  int bwd_kernel = 1;      // batched backward: 1 = [pixel][column] tile (lvl), 2 = [column][pixel] tile (cp)
   int bwd_rowmod = 2;      // shared-memory row length of that kernel, modulo 32 banks
   int build_pair = 0;      // CTA-pair build kernel (cross-check build only)
   int build_stages = 0;    // cap of the operand ring depth (0 = fill shared memory)

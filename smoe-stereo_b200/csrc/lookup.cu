@@ -376,102 +376,83 @@ struct BatchedGeom {
 #include "xcheck_lookup.cuh"
 #endif
 
-// Batched backward, current version: warp = (pyramid level, tap group), lane = pixel of the 32-pixel tile.
+// Second version of the batched backward: warp = pyramid level, lane = pixel of the 32-pixel tile.
 // The gradient rows of a pixel are private to it and the levels occupy disjoint parts of the row,
 // so the T iterations need NO barrier and no shared-memory staging of the gradient tiles: each warp
-// streams the gradient channels it needs (+ the coordinate) of iteration t straight from global
-// memory into registers -- lane = pixel makes every load one coalesced line -- several iterations
-// ahead of the one it is scattering.  No cp.async address arithmetic, no per-iteration
-// __syncthreads, no alignment requirement on the gradient planes.
-// NS = threads per (pixel, level): the 2r+2 = 10 window elements of a (pixel, level) are split into
-// NS disjoint tap groups handled by different warps (NS = 2: taps 0-4 / 5-9).  The groups touch
-// disjoint shared-memory words, so there is still no race and no barrier; every element still
-// receives exactly one contribution per iteration, iterations ascending => bit-identical results
-// for every NS.  What it buys: the kernel is bound by the dependent shared-memory
-// read-modify-write chain of each warp at an occupancy that the 45 KB of gradient rows per tile
-// cap at 5 CTAs per SM (profiles/r01/README.md); NS = 2 doubles the warps per SM (20 -> 40) for
-// the same shared memory and halves each chain.  Cost: the channel at a group boundary is loaded
-// by two warps (10 instead of 9 channel loads per level; an L1 hit).
-template <int NS> struct BwdSplit;
-template <> struct BwdSplit<1> { static constexpr int NT = 10, kDepth = 5, kMinBlocks = 5; };
-template <> struct BwdSplit<2> { static constexpr int NT = 5, kDepth = 3, kMinBlocks = 5; };   // <= 51 registers
-template <> struct BwdSplit<3> { static constexpr int NT = 4, kDepth = 3, kMinBlocks = 3; };
-
-template <typename GT, int NL, int NS>
-__global__ void __launch_bounds__(128 * NS, BwdSplit<NS>::kMinBlocks)
+// streams its 9 gradient channels (+ the coordinate) of iteration t straight from global memory
+// into registers -- lane = pixel makes every load one coalesced line -- two iterations ahead of
+// the one it is scattering.  One coordinate split per (pixel, level, iteration) instead of two,
+// no cp.async address arithmetic, no per-iteration __syncthreads: ~2.2x fewer warp-instructions
+// than lookup_bwd_batched_kernel, and no 16-byte alignment requirement on the gradient planes.
+// Same accumulation order per element (iterations ascending) => bit-identical results.
+template <typename GT, int NL>
+__global__ void __launch_bounds__(128)
 lookup_bwd_lvl_kernel(const __grid_constant__ BwdBatch batch, const BatchedGeom geo,
                       float* __restrict__ g0_out, long long g0_pitch, int HW, int accumulate) {
-  constexpr int R = 4, RD = 9, NC = NL * RD;
-  constexpr int NT = BwdSplit<NS>::NT;            // window elements per thread (at most)
-  constexpr int kDepth = BwdSplit<NS>::kDepth;    // register ring: kDepth-1 iterations in flight
-  constexpr int kThreads = 128 * NS;
+#ifndef SMOE_BWD_LVL_DEPTH
+#define SMOE_BWD_LVL_DEPTH 5
+#endif
+  constexpr int R = 4, RD = 9, NC = NL * RD, kDepth = SMOE_BWD_LVL_DEPTH;   // register ring: kDepth-1 iterations in flight
   extern __shared__ __align__(16) uint8_t s_raw[];
   float* s_rows = reinterpret_cast<float*>(s_raw);                    // [kTilePx][rowlen]
 
   pdl_launch_dependents();
   pdl_wait();
   const int tid = threadIdx.x;
-  const int warp = tid >> 5, lane = tid & 31;
-  const int l = warp & 3, part = warp >> 2;
+  const int l = tid >> 5, lane = tid & 31;
   const int b = blockIdx.y;
   const int hw0 = blockIdx.x * kTilePx;
   const int npx = min(kTilePx, HW - hw0);
 
-  for (int i = tid; i < kTilePx * geo.rowlen / 4; i += kThreads)
+  for (int i = tid; i < kTilePx * geo.rowlen / 4; i += 128)
     reinterpret_cast<float4*>(s_rows)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (accumulate) {
     __syncthreads();
     for (int pp = 0; pp < npx; ++pp)
-      for (int j = tid; j < geo.width[0]; j += kThreads)
+      for (int j = tid; j < geo.width[0]; j += 128)
         s_rows[pp * geo.rowlen + j] = g0_out[((long long)b * HW + hw0 + pp) * g0_pitch + j];
   }
   __syncthreads();
 
   if (l < NL && lane < npx) {
-    // this thread's window elements [t0, t0 + nt) and the gradient channels [t0-1, t0+nt-1] they use
-    const int t0 = NS == 1 ? 0 : (NS == 2 ? 5 * part : (part == 0 ? 0 : 3 * part + 1));
-    const int nt = NS == 3 ? (part == 0 ? 4 : 3) : NT;
-    float* rowl = s_rows + lane * geo.rowlen + geo.off[l] + t0;
+    float* rowl = s_rows + lane * geo.rowlen + geo.off[l];
     const unsigned width = (unsigned)geo.width[l];
     const float lscale = 1.0f / (float)(1 << l);
     const long long gofs = ((long long)b * NC + l * RD) * HW + hw0 + lane;
-    float g[kDepth][NT + 1], x[kDepth];
-    auto load = [&](int t, float (&gt)[NT + 1], float& xt) {
+    float g[kDepth][RD], x[kDepth];
+    auto load = [&](int t, float (&gt)[RD], float& xt) {
       const GT* gp = static_cast<const GT*>(batch.gout[t]) + gofs;
 #pragma unroll
-      for (int j = 0; j <= NT; ++j) {                 // gt[j] = channel t0-1+j (0 where it does not exist)
-        const int c = t0 - 1 + j;
-        gt[j] = (c >= 0 && c < RD && j <= nt) ? to_float(__ldg(gp + (long long)c * HW)) : 0.f;
-      }
+      for (int k = 0; k < RD; ++k) gt[k] = to_float(__ldg(gp + (long long)k * HW));
       xt = __ldg(batch.coords[t] + (long long)b * batch.coords_bstride[t] + hw0 + lane);
     };
-    auto scatter = [&](const float (&gt)[NT + 1], float xt) {
+    auto scatter = [&](const float (&gt)[RD], float xt) {
       int base;
       float dx;
       split_coord(xt * lscale, R, base, dx);
       // (a shared-memory atomicAdd per tap compiles to an ATOMS.CAST.SPIN loop on sm_100a: no gain)
-      float cur[NT];
-      bool ok[NT];
+      float cur[RD + 1];
+      bool ok[RD + 1];
 #pragma unroll
-      for (int k = 0; k < NT; ++k) {                  // all shared-memory loads first
-        ok[k] = k < nt && (unsigned)(base + t0 + k) < width;
+      for (int k = 0; k <= RD; ++k) {                 // all shared-memory loads first
+        ok[k] = (unsigned)(base + k) < width;
         cur[k] = ok[k] ? rowl[base + k] : 0.f;
       }
 #pragma unroll
-      for (int k = 0; k < NT; ++k)
-        cur[k] += BwdTap<float>::eval(gt[k], gt[k + 1], t0 + k > 0, t0 + k < RD, dx);
+      for (int k = 0; k <= RD; ++k)
+        cur[k] += BwdTap<float>::eval(k > 0 ? gt[k - 1] : 0.f, k < RD ? gt[k] : 0.f, k > 0, k < RD, dx);
 #pragma unroll
-      for (int k = 0; k < NT; ++k)
+      for (int k = 0; k <= RD; ++k)
         if (ok[k]) rowl[base + k] = cur[k];
     };
     const int T = batch.T;
 #pragma unroll
     for (int u = 0; u < kDepth - 1; ++u)
       if (u < T) load(u, g[u], x[u]);
-    for (int tt = 0; tt < T; tt += kDepth) {
+    for (int t0 = 0; t0 < T; t0 += kDepth) {
 #pragma unroll
       for (int u = 0; u < kDepth; ++u) {
-        const int t = tt + u;
+        const int t = t0 + u;
         if (t < T) {
           if (t + kDepth - 1 < T) load(t + kDepth - 1, g[(u + kDepth - 1) % kDepth], x[(u + kDepth - 1) % kDepth]);
           scatter(g[u], x[u]);
@@ -481,7 +462,7 @@ lookup_bwd_lvl_kernel(const __grid_constant__ BwdBatch batch, const BatchedGeom 
   }
   __syncthreads();                         // all scatters done before the fold reads the rows
   const int w0 = geo.width[0];
-  for (int j = tid; j < w0; j += kThreads) {
+  for (int j = tid; j < w0; j += 128) {
     int top = 0;
     for (int lv = 1; lv < NL; ++lv) {
       if ((j >> lv) >= geo.width[lv]) break;
@@ -496,6 +477,278 @@ lookup_bwd_lvl_kernel(const __grid_constant__ BwdBatch batch, const BatchedGeom 
       if (top >= 2) tsum = rowp[i2] + 0.5f * tsum;
       if (top >= 1) tsum = rowp[i1] + 0.5f * tsum;
       out[(long long)pp * g0_pitch] = rowp[j] + 0.5f * tsum;
+    }
+  }
+}
+
+// Third version: same warp = level / lane = pixel mapping and register streaming, but the tile is
+// stored [column][pixel] -- word (off_l + col) * 32 + pixel -- so the bank of every access is the
+// lane: the scatter is conflict-free WHATEVER the coordinates are.  In the [pixel][column] layout
+// above the bank is (pixel * rowlen + column) with data-dependent columns, i.e. random: ncu counted
+// 23.2 M shared-memory wavefronts for 10.7 M requests at config 2 and the L1/shared pipe, 62 % busy
+// with dependent read-modify-write chains, is what bounds the kernel (profiles/r01/README.md).
+// The price is the write-out: with lane = pixel a warp cannot write a row of the level-0 gradient
+// as one line, so every lane folds FOUR consecutive columns of its own pixel and stores them as one
+// 16-byte piece (32 lanes -> 32 rows -> 32 half sectors per instruction; the other half of each
+// sector follows from the same thread one step later, L2 merges them before the write-back).
+// Same arithmetic and accumulation order per element as the other versions => bit-identical.
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait_group() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// PROBE (cross-check builds, tools/variants_probe.py): 1 = stream the gradients but do not scatter
+// (what the global loads alone cost), 2 = scatter constants without loading anything (what the
+// shared-memory work alone costs).  0 = the real kernel.
+template <typename GT, int NL, int PROBE = 0>
+__global__ void __launch_bounds__(128)
+lookup_bwd_cp_kernel(const __grid_constant__ BwdBatch batch, const BatchedGeom geo,
+                     float* __restrict__ g0_out, long long g0_pitch, int HW, int accumulate) {
+  constexpr int R = 4, RD = 9, NC = NL * RD, kDepth = SMOE_BWD_LVL_DEPTH;
+  extern __shared__ __align__(16) uint8_t s_raw[];
+  float* s_t = reinterpret_cast<float*>(s_raw);                       // [geo.rowlen columns][kTilePx]
+
+  pdl_launch_dependents();
+  pdl_wait();
+  const int tid = threadIdx.x;
+  const int l = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.y;
+  const int hw0 = blockIdx.x * kTilePx;
+  const int npx = min(kTilePx, HW - hw0);
+  const int w0 = geo.width[0];
+
+  for (int i = tid; i < geo.rowlen * (kTilePx / 4); i += 128)
+    reinterpret_cast<float4*>(s_t)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (accumulate) {
+    __syncthreads();
+    if (lane < npx) {
+      const float* src = g0_out + ((long long)b * HW + hw0 + lane) * g0_pitch;
+      for (int j = l; j < w0; j += 4) s_t[j * kTilePx + lane] = src[j];
+    }
+  }
+  __syncthreads();
+
+  if (l < NL && lane < npx) {
+    float* coll = s_t + geo.off[l] * kTilePx + lane;
+    const unsigned width = (unsigned)geo.width[l];
+    const float lscale = 1.0f / (float)(1 << l);
+    const long long gofs = ((long long)b * NC + l * RD) * HW + hw0 + lane;
+    float g[kDepth][RD], x[kDepth];
+    float probe_acc = 0.f;
+    auto load = [&](int t, float (&gt)[RD], float& xt) {
+      if (PROBE == 2) {
+#pragma unroll
+        for (int k = 0; k < RD; ++k) gt[k] = 0.25f * (float)(k + t);
+        xt = (float)((hw0 + lane) % w0) - 0.37f * (float)t;
+        return;
+      }
+      const GT* gp = static_cast<const GT*>(batch.gout[t]) + gofs;
+#pragma unroll
+      for (int k = 0; k < RD; ++k) gt[k] = to_float(__ldg(gp + (long long)k * HW));
+      xt = __ldg(batch.coords[t] + (long long)b * batch.coords_bstride[t] + hw0 + lane);
+    };
+    auto scatter = [&](const float (&gt)[RD], float xt) {
+      if (PROBE == 1) {
+#pragma unroll
+        for (int k = 0; k < RD; ++k) probe_acc += gt[k];
+        probe_acc += xt;
+        return;
+      }
+      int base;
+      float dx;
+      split_coord(xt * lscale, R, base, dx);
+      float* win = coll + base * kTilePx;
+      float cur[RD + 1];
+      bool ok[RD + 1];
+#pragma unroll
+      for (int k = 0; k <= RD; ++k) {                 // all shared-memory loads first
+        ok[k] = (unsigned)(base + k) < width;
+        cur[k] = ok[k] ? win[k * kTilePx] : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k <= RD; ++k)
+        cur[k] += BwdTap<float>::eval(k > 0 ? gt[k - 1] : 0.f, k < RD ? gt[k] : 0.f, k > 0, k < RD, dx);
+#pragma unroll
+      for (int k = 0; k <= RD; ++k)
+        if (ok[k]) win[k * kTilePx] = cur[k];
+    };
+    const int T = batch.T;
+#pragma unroll
+    for (int u = 0; u < kDepth - 1; ++u)
+      if (u < T) load(u, g[u], x[u]);
+    for (int t0 = 0; t0 < T; t0 += kDepth) {
+#pragma unroll
+      for (int u = 0; u < kDepth; ++u) {
+        const int t = t0 + u;
+        if (t < T) {
+          if (t + kDepth - 1 < T) load(t + kDepth - 1, g[(u + kDepth - 1) % kDepth], x[(u + kDepth - 1) % kDepth]);
+          scatter(g[u], x[u]);
+        }
+      }
+    }
+    if (PROBE == 1) coll[0] = probe_acc;
+  }
+  __syncthreads();                         // all scatters done before the fold reads the tile
+  // fold + write-out: lane = pixel, a thread handles 4 consecutive level-0 columns at a time (they
+  // share G2[j/4], G3[j/8] and use G1[j/2], G1[j/2+1]); same chain as fold_grad_vec_kernel
+  if (lane < npx) {
+    const int w1 = NL > 1 ? geo.width[1] : 0, w2 = NL > 2 ? geo.width[2] : 0, w3 = NL > 3 ? geo.width[3] : 0;
+    const float* c0 = s_t + lane;
+    const float* c1 = s_t + geo.off[1] * kTilePx + lane;
+    const float* c2p = s_t + geo.off[2] * kTilePx + lane;
+    const float* c3 = s_t + geo.off[3] * kTilePx + lane;
+    float* orow = g0_out + ((long long)b * HW + hw0 + lane) * g0_pitch;
+    const bool vec = (g0_pitch & 3) == 0 && (reinterpret_cast<uintptr_t>(g0_out) & 15) == 0;
+    for (int j = 4 * l; j < w0; j += 16) {
+      const int m = j >> 1, q = j >> 2, o = j >> 3;
+      float v[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[e] = (j + e < w0) ? c0[(j + e) * kTilePx] : 0.f;
+      const float g1a = m < w1 ? c1[m * kTilePx] : 0.f;
+      const float g1b = m + 1 < w1 ? c1[(m + 1) * kTilePx] : 0.f;
+      const float g2 = q < w2 ? c2p[q * kTilePx] : 0.f;
+      const float g3 = (q < w2 && o < w3) ? c3[o * kTilePx] : 0.f;
+      const float t2 = q < w2 ? g2 + 0.5f * g3 : 0.f;
+      const float a0 = m < w1 ? g1a + 0.5f * t2 : 0.f;
+      const float a1 = m + 1 < w1 ? g1b + 0.5f * t2 : 0.f;
+      v[0] += 0.5f * a0; v[1] += 0.5f * a0; v[2] += 0.5f * a1; v[3] += 0.5f * a1;
+      if (vec) {                           // (rows are padded to the pitch: a tail piece may be stored whole)
+        *reinterpret_cast<float4*>(orow + j) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (j + e < w0) orow[j + e] = v[e];
+      }
+    }
+  }
+}
+
+// Fourth version: the [column][pixel] tile of lookup_bwd_cp_kernel, with the gradient stream moved
+// from a register ring to a THREAD-PRIVATE cp.async ring in shared memory.  ncu shows the register
+// version stalled on the long scoreboard (5.7 of 11.5 cycles per issued instruction) although four
+// iterations of loads are nominally in flight per warp, and its time does not change with the ring
+// depth: a warp has six scoreboards, the ring's load groups alias on them, and waiting for the
+// oldest group waits for the youngest too -- the software pipeline collapses.  cp.async groups are
+// counted, not scoreboarded: `cp.async.wait_group kStages-2` waits for exactly the oldest stage.
+// Each lane copies the 4-byte values of ITS pixel (9 channels of its level + the coordinate; the 32
+// lanes of a warp form one 128-byte line per copy instruction) and later reads back only what it
+// copied itself, so no barrier or warp synchronisation is involved at all.  fp32 gradients only
+// (cp.async moves >= 4 bytes); same arithmetic and order as the other versions => bit-identical.
+constexpr int kAsyncStages = 6;
+template <int NL>
+__global__ void __launch_bounds__(128)
+lookup_bwd_async_kernel(const __grid_constant__ BwdBatch batch, const BatchedGeom geo,
+                        float* __restrict__ g0_out, long long g0_pitch, int HW, int accumulate) {
+  constexpr int R = 4, RD = 9, NC = NL * RD, S = kAsyncStages;
+  extern __shared__ __align__(16) uint8_t s_raw[];
+  float* s_t = reinterpret_cast<float*>(s_raw);                       // [geo.rowlen columns][kTilePx]
+  float* s_ring = s_t + geo.rowlen * kTilePx;                         // [4 warps][S][RD + 1][kTilePx]
+
+  pdl_launch_dependents();
+  pdl_wait();
+  const int tid = threadIdx.x;
+  const int l = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.y;
+  const int hw0 = blockIdx.x * kTilePx;
+  const int npx = min(kTilePx, HW - hw0);
+  const int w0 = geo.width[0];
+  const bool worker = l < NL && lane < npx;
+  float* ring = s_ring + (l * S) * (RD + 1) * kTilePx + lane;
+  const long long gofs = ((long long)b * NC + l * RD) * HW + hw0 + lane;
+
+  auto issue = [&](int t) {
+    if (worker && t < batch.T) {
+      const float* gp = static_cast<const float*>(batch.gout[t]) + gofs;
+      const uint32_t dst = ptx_smem(ring + (t % S) * (RD + 1) * kTilePx);
+#pragma unroll
+      for (int k = 0; k < RD; ++k) cp_async4(dst + k * kTilePx * 4, gp + (long long)k * HW);
+      cp_async4(dst + RD * kTilePx * 4, batch.coords[t] + (long long)b * batch.coords_bstride[t] + hw0 + lane);
+    }
+    cp_async_commit_group();                          // exactly one group per iteration slot
+  };
+#pragma unroll
+  for (int t = 0; t < S - 1; ++t) issue(t);           // the stream starts before the tile is cleared
+
+  for (int i = tid; i < geo.rowlen * (kTilePx / 4); i += 128)
+    reinterpret_cast<float4*>(s_t)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (accumulate) {
+    __syncthreads();
+    if (lane < npx) {
+      const float* src = g0_out + ((long long)b * HW + hw0 + lane) * g0_pitch;
+      for (int j = l; j < w0; j += 4) s_t[j * kTilePx + lane] = src[j];
+    }
+  }
+  __syncthreads();
+
+  {
+    float* coll = s_t + geo.off[l < NL ? l : 0] * kTilePx + lane;
+    const unsigned width = (unsigned)geo.width[l < NL ? l : 0];
+    const float lscale = 1.0f / (float)(1 << l);
+    const int T = batch.T;
+    for (int t = 0; t < T; ++t) {
+      cp_async_wait_group<S - 2>();                   // groups 0..t have landed (t+1 .. t+S-2 may be in flight)
+      float gt[RD], xt = 0.f;
+      const float* src = ring + (t % S) * (RD + 1) * kTilePx;
+      if (worker) {
+#pragma unroll
+        for (int k = 0; k < RD; ++k) gt[k] = src[k * kTilePx];
+        xt = src[RD * kTilePx];
+      }
+      issue(t + S - 1);                               // refills the slot consumed in the previous iteration
+      if (worker) {
+        int base;
+        float dx;
+        split_coord(xt * lscale, R, base, dx);
+        float* win = coll + base * kTilePx;
+        float cur[RD + 1];
+        bool ok[RD + 1];
+#pragma unroll
+        for (int k = 0; k <= RD; ++k) {
+          ok[k] = (unsigned)(base + k) < width;
+          cur[k] = ok[k] ? win[k * kTilePx] : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k <= RD; ++k)
+          cur[k] += BwdTap<float>::eval(k > 0 ? gt[k - 1] : 0.f, k < RD ? gt[k] : 0.f, k > 0, k < RD, dx);
+#pragma unroll
+        for (int k = 0; k <= RD; ++k)
+          if (ok[k]) win[k * kTilePx] = cur[k];
+      }
+    }
+  }
+  cp_async_wait_group<0>();
+  __syncthreads();                         // all scatters done before the fold reads the tile
+  if (lane < npx) {
+    const int w1 = NL > 1 ? geo.width[1] : 0, w2 = NL > 2 ? geo.width[2] : 0, w3 = NL > 3 ? geo.width[3] : 0;
+    const float* c0 = s_t + lane;
+    const float* c1 = s_t + geo.off[1] * kTilePx + lane;
+    const float* c2p = s_t + geo.off[2] * kTilePx + lane;
+    const float* c3 = s_t + geo.off[3] * kTilePx + lane;
+    float* orow = g0_out + ((long long)b * HW + hw0 + lane) * g0_pitch;
+    const bool vec = (g0_pitch & 3) == 0 && (reinterpret_cast<uintptr_t>(g0_out) & 15) == 0;
+    for (int j = 4 * l; j < w0; j += 16) {
+      const int m = j >> 1, q = j >> 2, o = j >> 3;
+      float v[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[e] = (j + e < w0) ? c0[(j + e) * kTilePx] : 0.f;
+      const float g1a = m < w1 ? c1[m * kTilePx] : 0.f;
+      const float g1b = m + 1 < w1 ? c1[(m + 1) * kTilePx] : 0.f;
+      const float g2 = q < w2 ? c2p[q * kTilePx] : 0.f;
+      const float g3 = (q < w2 && o < w3) ? c3[o * kTilePx] : 0.f;
+      const float t2 = q < w2 ? g2 + 0.5f * g3 : 0.f;
+      const float a0 = m < w1 ? g1a + 0.5f * t2 : 0.f;
+      const float a1 = m + 1 < w1 ? g1b + 0.5f * t2 : 0.f;
+      v[0] += 0.5f * a0; v[1] += 0.5f * a0; v[2] += 0.5f * a1; v[3] += 0.5f * a1;
+      if (vec) {
+        *reinterpret_cast<float4*>(orow + j) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (j + e < w0) orow[j + e] = v[e];
+      }
     }
   }
 }
@@ -615,8 +868,8 @@ constexpr bool kXcheck = true;
 static int fwd_kernel_choice() { return 0; }
 constexpr bool kXcheck = false;
 #endif
-constexpr int kDefaultPxHint = 1;        // level-0 fills evict_first (Tuning::px_hint)
-constexpr int kDefaultBwdSplit = 2;      // Tuning::bwd_split
+constexpr int kStreamPxHint = 5;         // volumes >> L2: level-0 fills and output stores evict_first
+constexpr int kDefaultBwdKernel = 1;     // Tuning::bwd_kernel: 1 = lookup_bwd_lvl_kernel, 2 = lookup_bwd_cp_kernel
 
 // The 256-bit path reads whole 32-byte chunks aligned in MEMORY: the first chunk of a level may
 // begin 16 bytes before the level and the last may end 16 bytes after its row.  That stays inside
@@ -663,17 +916,25 @@ static void launch_fwd_px(const PyrDev& d, const float* coords, long long cbs, f
         return;
       }
 #define SMOE_PX256(H) launch_kernel_pdl(lookup_fwd_px_kernel<VT, OT, 4, NL, true, kSplit, true, H>, grid, block, 0, st, d, coords, cbs, cs, o, HW, upd)
+      // L2 eviction priorities (variants_probe.py, 32 distinct outputs per graph): for a volume several
+      // times the L2 (cfg3, 600 MB) marking the level-0 fills AND the output stores evict_first gives
+      // 20.5 -> 17.0-17.9 us; at 166 MB (cfg2), where most of level 0 still finds room in L2, any
+      // hint on level 0 costs 5-10 %, and at 2.2 GB (cfg4) nothing moves outside the noise.
+      const bool huge = (long long)HW * B * d.pitch[0] * (long long)sizeof(VT) > (256ll << 20);
+      const int hint = (kXcheck && tn.px_hint >= 0) ? tn.px_hint : (huge ? kStreamPxHint : 0);
       if constexpr (kXcheck) {
-        switch (tn.px_hint) {
-          case 0: SMOE_PX256(0); break;
+        switch (hint) {
+          case 1: SMOE_PX256(1); break;
           case 2: SMOE_PX256(2); break;
           case 3: SMOE_PX256(3); break;
+          case 4: SMOE_PX256(4); break;
           case 5: SMOE_PX256(5); break;
           case 6: SMOE_PX256(6); break;
-          default: SMOE_PX256(kDefaultPxHint); break;
+          case 7: SMOE_PX256(7); break;
+          default: SMOE_PX256(0); break;
         }
       } else {
-        SMOE_PX256(kDefaultPxHint);
+        if (hint == kStreamPxHint) SMOE_PX256(kStreamPxHint); else SMOE_PX256(0);
       }
 #undef SMOE_PX256
       return;
@@ -972,33 +1233,45 @@ int smoe_corr_lookup_bwd_batched(const smoe_pyramid_t* g0, int num_levels, int n
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   dim3 grid((unsigned)((HW + kTilePx - 1) / kTilePx), g0->B);
   float* out = static_cast<float*>(g0->level_ptr[0]);
-  const int ns = kXcheck ? tuning().bwd_split : kDefaultBwdSplit;
-#define SMOE_LAUNCH_LVL(GT, NLV, NSV)                                                                    \
+  const int which = kXcheck ? tuning().bwd_kernel : kDefaultBwdKernel;   // 1 = [pixel][column], 2 = [column][pixel]
+  bool async = which == 3 && !staged && grad_out_dtype == SMOE_DTYPE_F32;
+  if ((which == 2 || which == 3) && !staged) {
+    geo.rowlen = off;                       // columns of the [column][pixel] tile
+    smem = (size_t)kTilePx * off * 4;
+    const size_t ring = (size_t)4 * kAsyncStages * 10 * kTilePx * 4;
+    if (async && smem + ring <= 227 * 1024) smem += ring; else async = false;
+  }
+#define SMOE_LAUNCH_ASYNC(NLV)                                                                           \
   do {                                                                                                   \
-    SMOE_CUDA_OK(cudaFuncSetAttribute(lookup_bwd_lvl_kernel<GT, NLV, NSV>,                               \
+    SMOE_CUDA_OK(cudaFuncSetAttribute(lookup_bwd_async_kernel<NLV>,                                      \
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
-    SMOE_CUDA_OK(launch_kernel(lookup_bwd_lvl_kernel<GT, NLV, NSV>, grid, dim3(128 * NSV), smem, st,     \
-                               batch, geo, out, (long long)g0->pitch[0], (int)HW, accumulate));           \
+    SMOE_CUDA_OK(launch_kernel(lookup_bwd_async_kernel<NLV>, grid, dim3(128), smem, st, batch, geo, out, \
+                               (long long)g0->pitch[0], (int)HW, accumulate));                           \
   } while (0)
+#define SMOE_LAUNCH_FN(FN, THREADS)                                                                      \
+  do {                                                                                                   \
+    SMOE_CUDA_OK(cudaFuncSetAttribute(FN, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+    SMOE_CUDA_OK(launch_kernel(FN, grid, dim3(THREADS), smem, st, batch, geo, out,                       \
+                               (long long)g0->pitch[0], (int)HW, accumulate));                           \
+  } while (0)
+#define SMOE_LAUNCH_KERN(KERN, GT, NLV, THREADS) SMOE_LAUNCH_FN((KERN<GT, NLV>), THREADS)
 #ifdef SMOE_CROSSCHECK
 #define SMOE_LAUNCH_BATCHED(GT, NLV)                                                                     \
   do {                                                                                                   \
-    if (staged) {                                                                                        \
-      SMOE_CUDA_OK(cudaFuncSetAttribute(lookup_bwd_batched_kernel<GT, NLV>,                              \
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
-      SMOE_CUDA_OK(launch_kernel(lookup_bwd_batched_kernel<GT, NLV>, grid, dim3(kBatchedThreads), smem,  \
-                                 st, batch, geo, out, (long long)g0->pitch[0], (int)HW, accumulate));     \
-    } else if (ns == 1) {                                                                                \
-      SMOE_LAUNCH_LVL(GT, NLV, 1);                                                                       \
-    } else if (ns == 3) {                                                                                \
-      SMOE_LAUNCH_LVL(GT, NLV, 3);                                                                       \
-    } else {                                                                                             \
-      SMOE_LAUNCH_LVL(GT, NLV, 2);                                                                       \
-    }                                                                                                    \
+    if (staged) SMOE_LAUNCH_KERN(lookup_bwd_batched_kernel, GT, NLV, kBatchedThreads);                   \
+    else if (async) SMOE_LAUNCH_ASYNC(NLV);                                                              \
+    else if (which == 11) SMOE_LAUNCH_FN((lookup_bwd_cp_kernel<GT, NLV, 1>), 128);                       \
+    else if (which == 12) SMOE_LAUNCH_FN((lookup_bwd_cp_kernel<GT, NLV, 2>), 128);                       \
+    else if (which >= 2) SMOE_LAUNCH_KERN(lookup_bwd_cp_kernel, GT, NLV, 128);                           \
+    else SMOE_LAUNCH_KERN(lookup_bwd_lvl_kernel, GT, NLV, 128);                                          \
   } while (0)
 #else
-#define SMOE_LAUNCH_BATCHED(GT, NLV) SMOE_LAUNCH_LVL(GT, NLV, kDefaultBwdSplit)
-  (void)ns;
+#define SMOE_LAUNCH_BATCHED(GT, NLV)                                                                     \
+  do {                                                                                                   \
+    if (async) SMOE_LAUNCH_ASYNC(NLV);                                                                   \
+    else if (kDefaultBwdKernel >= 2) SMOE_LAUNCH_KERN(lookup_bwd_cp_kernel, GT, NLV, 128);               \
+    else SMOE_LAUNCH_KERN(lookup_bwd_lvl_kernel, GT, NLV, 128);                                          \
+  } while (0)
 #endif
   const bool f16g = grad_out_dtype == SMOE_DTYPE_F16;
   switch (num_levels) {
@@ -1008,7 +1281,9 @@ int smoe_corr_lookup_bwd_batched(const smoe_pyramid_t* g0, int num_levels, int n
     default: if (f16g) SMOE_LAUNCH_BATCHED(__half, 4); else SMOE_LAUNCH_BATCHED(float, 4); break;
   }
 #undef SMOE_LAUNCH_BATCHED
-#undef SMOE_LAUNCH_LVL
+#undef SMOE_LAUNCH_KERN
+#undef SMOE_LAUNCH_FN
+#undef SMOE_LAUNCH_ASYNC
   return check_launch("lookup backward (batched)");
 }
 

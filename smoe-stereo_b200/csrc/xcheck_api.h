@@ -26,7 +26,7 @@ void smoe_corr_debug_set_lookup_kernel(int which);
 
 /*
  * Set one launch-tuning field (struct Tuning, csrc/common.cuh) by name for the whole process:
- * "bwd_split", "px_hint", "build_pair", "bwd_staged", "conv_lanes", ...  Returns 0, or 1 for an
+ * "bwd_kernel", "px_hint", "build_pair", "bwd_staged", "conv_lanes", ...  Returns 0, or 1 for an
  * unknown name.  Replaces the SMOE_CORR_* environment switches when a test or probe wants to compare
  * variants inside one process.
  */

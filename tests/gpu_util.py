@@ -74,8 +74,8 @@ class xcheck_lib:
 
     def __exit__(self, *exc):
         from smoe_stereo_b200 import _lib, corr
-        defaults = dict(pdl=2, fwd_kernel=0, px_tpb=32, px_split=1, px_ld256=-1, px_hint=1, lookup_tile=32,
-                        bwd_staged=0, bwd_split=2, bwd_rowmod=2, build_pair=0, build_stages=0, build_debug=0,
+        defaults = dict(pdl=2, fwd_kernel=0, px_tpb=32, px_split=1, px_ld256=-1, px_hint=-1, lookup_tile=32,
+                        bwd_staged=0, bwd_kernel=1, bwd_rowmod=2, build_pair=0, build_stages=0, build_debug=0,
                         conv_lanes=0)
         for k in self.tuning:
             self.L.smoe_corr_debug_set_tuning(k.encode(), defaults[k])

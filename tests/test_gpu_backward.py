@@ -131,6 +131,8 @@ def test_bwd_linearity_and_adjoint_full_size(sb):
     (1, 256, 3, 240, 240),     # config 1 width
     (1, 100, 2, 72, 136),      # C not a multiple of 16, W1 != W2, K tails
     (1, 300, 2, 40, 312),      # C > 256 -> two N tiles; W2 > 256 -> three M tiles in GEMM 1
+    (1, 64, 3, 37, 50),        # W % 4 != 0: pitch-padded operands (no torch.einsum fallback any more)
+    (1, 48, 2, 30, 750),       # BASELINE config 4 width (W/4 = 750)
 ])
 def test_native_build_backward_vs_oracle(sb, oracle, shape):
     """smoe_corr_build_bwd (tcgen05 tf32) == autograd of the einsum (core/corr.py:154-156)."""
@@ -184,6 +186,37 @@ def test_batched_backward_equals_accumulate_then_fold(sb, shape, T, gdtype):
         assert torch.equal(a, b)
     else:                       # two chunks are folded separately: same math, different rounding
         assert rel_max(a.cpu().numpy(), b.cpu().numpy()) < 1e-6
+    # every batched kernel of the cross-check library gives the same bits as the product's:
+    # [pixel][column] tile (lvl), [column][pixel] tile (cp), cp.async-staged first version
+    from gpu_util import xcheck_lib
+    for tuning in (dict(bwd_kernel=1), dict(bwd_kernel=2), dict(bwd_kernel=3), dict(bwd_staged=1)):
+        ges = 2 if gdtype == torch.float16 else 4
+        if "bwd_staged" in tuning and ((H * W * ges) % 16 or (2 * H * W) % 4):
+            continue            # the staged kernel needs 16-byte-multiple gradient / coordinate planes
+        with xcheck_lib(**tuning):
+            other = _batched_lookup_backward(pyr, items, 4, None)
+        assert torch.equal(other.level(0), a), tuning
+
+
+@pytest.mark.parametrize("levels,W", [(1, 40), (2, 37), (3, 50), (4, 9)])
+def test_batched_kernels_agree_for_fewer_levels_and_accumulate(sb, levels, W):
+    """1-4 levels, odd / tiny widths, and accumulate=1 on top of an existing level-0 gradient."""
+    from gpu_util import dev, make_coords, xcheck_lib
+    from smoe_stereo_b200.corr import _batchable, _batched_lookup_backward
+    B, H, T = 2, 5, 3
+    gen = torch.Generator(device="cpu").manual_seed(W)
+    coords = [torch.from_numpy(make_coords(B, H, W, W, 1, seed=7 + t)[0]).to(dev()) for t in range(T)]
+    gouts = [torch.randn(B, 9 * levels, H, W, generator=gen).to(dev()) for _ in range(T)]
+    pyr = sb.FusedPyramid(B, H, W, W, levels, torch.float32, dev())
+    items = [_batchable(pyr, c, g, 4) for c, g in zip(coords, gouts)]
+    res = []
+    for which in (1, 2, 3):
+        with xcheck_lib(bwd_kernel=which):
+            g0 = _batched_lookup_backward(pyr, items[:2], 4, None)
+            g0 = _batched_lookup_backward(pyr, items[2:], 4, g0)          # accumulate = 1
+        res.append(g0.level(0).clone())
+    assert torch.equal(res[0], res[1]) and torch.equal(res[0], res[2])
+    assert torch.isfinite(res[0]).all() and res[0].abs().sum() > 0
 
 
 def test_batched_and_per_call_paths_mix(sb):
