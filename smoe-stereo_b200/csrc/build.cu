@@ -621,6 +621,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 EncodeTiledFn tensor_map_encoder();   // shared with build_bwd.cu
 static EncodeTiledFn encode_fn() { return tensor_map_encoder(); }
+void* tensor_map_encoder_ptr() { return reinterpret_cast<void*>(tensor_map_encoder()); }   // for lookup.cu
 EncodeTiledFn tensor_map_encoder() {
   static EncodeTiledFn fn = [] {
     void* p = nullptr;

@@ -18,14 +18,18 @@
 //  * backward, overwrite: one pass writes every element of the dense gradient (zeros outside the
 //    window), replacing the reference's zeros_like + scatter pair (sampler_kernel.cu:148-163).
 //  * generic scalar kernels cover unaligned widths / pitches and radii other than 4.
+#include <cuda.h>
 #include <stdlib.h>
 
 #include <type_traits>
 
 #include "common.cuh"
+#include "ptx.cuh"
 #include "px_gather.cuh"
 
 namespace smoe {
+
+void* tensor_map_encoder_ptr();   // build.cu: cuTensorMapEncodeTiled from the driver (no link-time libcuda dependency)
 
 __device__ __forceinline__ uint32_t ptx_smem(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -753,6 +757,193 @@ lookup_bwd_async_kernel(const __grid_constant__ BwdBatch batch, const BatchedGeo
   }
 }
 
+// Fifth version (the product's default for fp32 gradients): the [column][pixel] tile, fed by a TMA
+// producer warp, written out through a transposing staging tile.
+// What the probes of lookup_bwd_cp_kernel showed at config 2 (tools/variants_probe.py): streaming the
+// 383 MB of gradients with per-lane loads takes 130 us on its own -- warps cannot keep more than
+// about one iteration of loads in flight, whether the ring lives in registers (scoreboards) or in
+// cp.async groups (three CTAs per SM) -- and scatter + fold + write-out take 75 us on their own.
+// So:  (1) warp 4 is a PRODUCER: per (tile, iteration) ONE tensor-map TMA load brings the [NC
+// channels x 32 pixels] gradient box (3-D map {H*W1, NC, B} over grad_out[t], encoded per launch;
+// tails zero-filled) and one 128-byte bulk copy the coordinates, completion counted in bytes on
+// an mbarrier, into a kStages-deep ring; kStages-1 iterations (4.7 KB each) are in flight per CTA
+// with no register, scoreboard or LSU-queue cost, and the stream starts before the tile is
+// cleared.  (One bulk copy PER ROW instead of the tensor map -- 37 requests per stage -- made the
+// kernel 2x slower than the register ring, 297 us: ~29 cycles of TMA issue per 128-byte request.)  (2) warps 0..3 are CONSUMERS
+// (warp = level, lane = pixel): wait for the stage, read their 10 values (lane == bank), release the
+// stage with one arrive per warp, scatter conflict-free into the [column][pixel] tile.  (3) the
+// write-out folds 4 columns at a time with lane = pixel, transposes 32x32 blocks through a padded
+// staging tile (carved out of the ring, idle by then) and stores whole 128-byte row segments.
+// Same arithmetic and accumulation order per element as every other version => bit-identical.
+constexpr int kTmaStages = 6;
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_init_(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+
+struct BwdTmaMaps {
+  CUtensorMap gout[kMaxBatchedIters];     // grad_out[t] as {H*W1, NC, B} fp32, box {32, NC, 1}
+};
+
+template <int NL>
+__global__ void __launch_bounds__(160)
+lookup_bwd_tma_kernel(const __grid_constant__ BwdBatch batch, const __grid_constant__ BwdTmaMaps maps,
+                      const BatchedGeom geo, float* __restrict__ g0_out, long long g0_pitch, int HW,
+                      int accumulate) {
+  constexpr int R = 4, RD = 9, NC = NL * RD, ROWS = NC + 1, S = kTmaStages;
+  extern __shared__ __align__(16) uint8_t s_raw[];
+  __shared__ __align__(8) uint64_t s_full[S], s_empty[S];
+  // TMA tensor loads want 128-byte aligned destinations: align the dynamic part by hand
+  float* s_t = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(s_raw) + 127) & ~(uintptr_t)127);   // [geo.rowlen columns][kTilePx]
+  float* s_ring = s_t + geo.rowlen * kTilePx;                         // [S][ROWS][kTilePx]; later staging
+
+  pdl_launch_dependents();
+  pdl_wait();
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.y;
+  const int hw0 = blockIdx.x * kTilePx;
+  const int npx = min(kTilePx, HW - hw0);
+  const int w0 = geo.width[0];
+  const int T = batch.T;
+  const uint32_t row_bytes = (uint32_t)npx * 4u;                      // a multiple of 16 (HW % 4 == 0)
+
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < S; ++i) {
+      mbar_init_(ptx_smem(&s_full[i]), 1);
+      mbar_init_(ptx_smem(&s_empty[i]), NL);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  auto produce = [&](int t) {                         // one lane of the producer warp
+    if (lane == 0) {
+      const int slot = t % S;
+      const uint32_t bar = ptx_smem(&s_full[slot]);
+      const uint32_t dst = ptx_smem(s_ring + (long long)slot * ROWS * kTilePx);
+      mbar_expect_tx_(bar, NC * kTilePx * 4 + row_bytes);          // the box counts in full, tails included
+      ptx::tma_load_3d(dst, &maps.gout[t], bar, hw0, 0, b);
+      bulk_copy_g2s(dst + NC * kTilePx * 4, batch.coords[t] + (long long)b * batch.coords_bstride[t] + hw0,
+                    row_bytes, bar);
+    }
+  };
+  if (warp == 4) {
+    for (int t = 0; t < S && t < T; ++t) produce(t);  // the stream starts before the tile is cleared
+  }
+  for (int i = tid; i < geo.rowlen * (kTilePx / 4); i += 160)
+    reinterpret_cast<float4*>(s_t)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (accumulate) {
+    __syncthreads();
+    if (lane < npx && warp < 4) {
+      const float* src = g0_out + ((long long)b * HW + hw0 + lane) * g0_pitch;
+      for (int j = warp; j < w0; j += 4) s_t[j * kTilePx + lane] = src[j];
+    }
+  }
+  __syncthreads();
+
+  if (warp == 4) {
+    for (int t = S; t < T; ++t) {
+      mbar_wait_(ptx_smem(&s_empty[t % S]), (uint32_t)((t / S) - 1) & 1u);
+      produce(t);
+    }
+  } else if (warp < NL) {
+    const int l = warp;
+    float* coll = s_t + geo.off[l] * kTilePx + lane;
+    const unsigned width = (unsigned)geo.width[l];
+    const float lscale = 1.0f / (float)(1 << l);
+    const bool worker = lane < npx;
+    for (int t = 0; t < T; ++t) {
+      const int slot = t % S;
+      mbar_wait_(ptx_smem(&s_full[slot]), (uint32_t)(t / S) & 1u);
+      const float* src = s_ring + ((long long)slot * ROWS) * kTilePx + lane;
+      float gt[RD], xt = 0.f;
+#pragma unroll
+      for (int k = 0; k < RD; ++k) gt[k] = worker ? src[(l * RD + k) * kTilePx] : 0.f;
+      if (worker) xt = src[NC * kTilePx];
+      __syncwarp();
+      if (lane == 0) mbar_arrive_(ptx_smem(&s_empty[slot]));       // this warp is done with the stage
+      if (worker) {
+        int base;
+        float dx;
+        split_coord(xt * lscale, R, base, dx);
+        float* win = coll + base * kTilePx;
+        float cur[RD + 1];
+        bool ok[RD + 1];
+#pragma unroll
+        for (int k = 0; k <= RD; ++k) {
+          ok[k] = (unsigned)(base + k) < width;
+          cur[k] = ok[k] ? win[k * kTilePx] : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k <= RD; ++k)
+          cur[k] += BwdTap<float>::eval(k > 0 ? gt[k - 1] : 0.f, k < RD ? gt[k] : 0.f, k > 0, k < RD, dx);
+#pragma unroll
+        for (int k = 0; k <= RD; ++k)
+          if (ok[k]) win[k * kTilePx] = cur[k];
+      }
+    }
+  }
+  __syncthreads();                         // all scatters done, every bulk copy has been consumed
+  // fold (same chain as fold_grad_vec_kernel, lane = pixel, 4 columns at a time) + transposing write-out
+  if (warp < 4) {
+    const int w1 = NL > 1 ? geo.width[1] : 0, w2 = NL > 2 ? geo.width[2] : 0, w3 = NL > 3 ? geo.width[3] : 0;
+    const float* c0 = s_t + lane;
+    const float* c1 = s_t + geo.off[1] * kTilePx + lane;
+    const float* c2p = s_t + geo.off[2] * kTilePx + lane;
+    const float* c3 = s_t + geo.off[3] * kTilePx + lane;
+    float* stg = s_ring + warp * (kTilePx * 33);                       // [32 pixels][33]
+    float* orow0 = g0_out + ((long long)b * HW + hw0) * g0_pitch;
+    for (int j0 = 32 * warp; j0 < w0; j0 += 128) {
+#pragma unroll 2
+      for (int c = 0; c < 32; c += 4) {
+        const int j = j0 + c;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (j < w0) {
+          const int m = j >> 1, q = j >> 2, o = j >> 3;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[e] = (j + e < w0) ? c0[(j + e) * kTilePx] : 0.f;
+          const float g1a = m < w1 ? c1[m * kTilePx] : 0.f;
+          const float g1b = m + 1 < w1 ? c1[(m + 1) * kTilePx] : 0.f;
+          const float g2 = q < w2 ? c2p[q * kTilePx] : 0.f;
+          const float g3 = (q < w2 && o < w3) ? c3[o * kTilePx] : 0.f;
+          const float t2 = q < w2 ? g2 + 0.5f * g3 : 0.f;
+          const float a0 = m < w1 ? g1a + 0.5f * t2 : 0.f;
+          const float a1 = m + 1 < w1 ? g1b + 0.5f * t2 : 0.f;
+          v[0] += 0.5f * a0; v[1] += 0.5f * a0; v[2] += 0.5f * a1; v[3] += 0.5f * a1;
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) stg[lane * 33 + c + e] = v[e];     // bank (lane + c + e) % 32: conflict-free
+      }
+      __syncwarp();
+      const int j = j0 + lane;
+      if (j < w0) {
+        float* dst = orow0 + j;
+        for (int p = 0; p < npx; ++p, dst += g0_pitch)                  // one 128-byte row segment per store
+          *dst = stg[p * 33 + lane];
+      }
+      __syncwarp();
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------------- fold
 // G0[j] += 0.5*(G1[j/2] + 0.5*(G2[j/4] + 0.5*G3[j/8])), stopping at the first level whose index
 // falls outside its width (the column an odd level dropped, core/corr.py:124).
@@ -1235,12 +1426,45 @@ int smoe_corr_lookup_bwd_batched(const smoe_pyramid_t* g0, int num_levels, int n
   float* out = static_cast<float*>(g0->level_ptr[0]);
   const int which = kXcheck ? tuning().bwd_kernel : kDefaultBwdKernel;   // 1 = [pixel][column], 2 = [column][pixel]
   bool async = which == 3 && !staged && grad_out_dtype == SMOE_DTYPE_F32;
-  if ((which == 2 || which == 3) && !staged) {
+  bool tma = which == 4 && !staged && grad_out_dtype == SMOE_DTYPE_F32 && HW % 4 == 0;
+  for (int t = 0; tma && t < num_iters; ++t)       // bulk copies: 16-byte aligned rows
+    tma = aligned16(coords[t]) && aligned16(grad_out[t]) && coords_batch_stride[t] % 4 == 0;
+  if (which >= 2 && !staged) {
     geo.rowlen = off;                       // columns of the [column][pixel] tile
     smem = (size_t)kTilePx * off * 4;
     const size_t ring = (size_t)4 * kAsyncStages * 10 * kTilePx * 4;
     if (async && smem + ring <= 227 * 1024) smem += ring; else async = false;
+    size_t tring = (size_t)kTmaStages * (num_levels * 9 + 1) * kTilePx * 4;
+    if (tring < (size_t)4 * kTilePx * 33 * 4) tring = (size_t)4 * kTilePx * 33 * 4;   // doubles as the staging tiles
+    if (tma && smem + tring + 256 <= 227 * 1024) smem += tring + 128; else tma = false;
   }
+  BwdTmaMaps maps;
+  if (tma) {
+    typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                      CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                      CUtensorMapFloatOOBfill);
+    EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(tensor_map_encoder_ptr());
+    SMOE_REQUIRE(enc != nullptr, SMOE_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    const int nc = num_levels * 9;
+    const cuuint64_t gdim[3] = {(cuuint64_t)HW, (cuuint64_t)nc, (cuuint64_t)g0->B};
+    const cuuint64_t gstr[2] = {(cuuint64_t)HW * 4, (cuuint64_t)nc * HW * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)kTilePx, (cuuint32_t)nc, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    for (int t = 0; t < num_iters; ++t) {
+      const CUresult r = enc(&maps.gout[t], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(grad_out[t]), gdim,
+                             gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      SMOE_REQUIRE(r == CUDA_SUCCESS, SMOE_ERR_CUDA, "lookup_bwd_batched: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    }
+  }
+#define SMOE_LAUNCH_TMA(NLV)                                                                             \
+  do {                                                                                                   \
+    SMOE_CUDA_OK(cudaFuncSetAttribute(lookup_bwd_tma_kernel<NLV>,                                        \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
+    SMOE_CUDA_OK(launch_kernel(lookup_bwd_tma_kernel<NLV>, grid, dim3(160), smem, st, batch, maps, geo,  \
+                               out, (long long)g0->pitch[0], (int)HW, accumulate));                      \
+  } while (0)
 #define SMOE_LAUNCH_ASYNC(NLV)                                                                           \
   do {                                                                                                   \
     SMOE_CUDA_OK(cudaFuncSetAttribute(lookup_bwd_async_kernel<NLV>,                                      \
@@ -1260,6 +1484,7 @@ int smoe_corr_lookup_bwd_batched(const smoe_pyramid_t* g0, int num_levels, int n
   do {                                                                                                   \
     if (staged) SMOE_LAUNCH_KERN(lookup_bwd_batched_kernel, GT, NLV, kBatchedThreads);                   \
     else if (async) SMOE_LAUNCH_ASYNC(NLV);                                                              \
+    else if (tma) SMOE_LAUNCH_TMA(NLV);                                                                  \
     else if (which == 11) SMOE_LAUNCH_FN((lookup_bwd_cp_kernel<GT, NLV, 1>), 128);                       \
     else if (which == 12) SMOE_LAUNCH_FN((lookup_bwd_cp_kernel<GT, NLV, 2>), 128);                       \
     else if (which >= 2) SMOE_LAUNCH_KERN(lookup_bwd_cp_kernel, GT, NLV, 128);                           \
@@ -1269,6 +1494,7 @@ int smoe_corr_lookup_bwd_batched(const smoe_pyramid_t* g0, int num_levels, int n
 #define SMOE_LAUNCH_BATCHED(GT, NLV)                                                                     \
   do {                                                                                                   \
     if (async) SMOE_LAUNCH_ASYNC(NLV);                                                                   \
+    else if (tma) SMOE_LAUNCH_TMA(NLV);                                                                  \
     else if (kDefaultBwdKernel >= 2) SMOE_LAUNCH_KERN(lookup_bwd_cp_kernel, GT, NLV, 128);               \
     else SMOE_LAUNCH_KERN(lookup_bwd_lvl_kernel, GT, NLV, 128);                                          \
   } while (0)
@@ -1284,6 +1510,7 @@ int smoe_corr_lookup_bwd_batched(const smoe_pyramid_t* g0, int num_levels, int n
 #undef SMOE_LAUNCH_KERN
 #undef SMOE_LAUNCH_FN
 #undef SMOE_LAUNCH_ASYNC
+#undef SMOE_LAUNCH_TMA
   return check_launch("lookup backward (batched)");
 }
 

@@ -65,6 +65,7 @@ def probe_bwd(L):
     ref = None
     for which, name in ((1, "lvl   [pixel][column], register ring"), (2, "cp    [column][pixel], register ring"),
                         (3, "async [column][pixel], cp.async ring  "),
+                        (4, "tma   [column][pixel], TMA producer   "),
                         (11, "PROBE cp: gradient loads only        "), (12, "PROBE cp: scatter + fold only        ")):
         L.smoe_corr_debug_set_tuning(b"bwd_kernel", which)
         hold = {}
