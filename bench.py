@@ -749,27 +749,26 @@ def main():
                 dst.copy_(src, non_blocking=True)
             in_ready[slot].record(h2d_stream)
 
+    # device-side staging for the lookup results of a pair: the caller owns these buffers (out=), so
+    # the loop never touches the caching allocator and never blocks the host; reuse of a slot is
+    # ordered on the device (compute stream waits for the D2H copies of pair i-2 out of that slot)
+    out_dev = [torch.empty((iters, B, L * (2 * r + 1), H, W), dtype=torch.float32, device=dev) for _ in range(2)]
+
     def compute(i, with_kernels=True):
         slot = i % 2
         f1, f2, c = dbuf[slot]
-        oh = out_host[slot]
-        # a double-buffered host loop may not refill out_host[slot] before the consumer has had pair
-        # i-2's results: the HOST waits here, which also bounds the lookup outputs in flight (without it
-        # the host enqueues all pairs at once and the caching allocator grows by cudaMalloc inside the
-        # timed region: 34 instead of 313 pairs/s on one box)
-        if i >= 2:
-            out_free[slot].synchronize()
+        oh, od = out_host[slot], out_dev[slot]
         stream.wait_event(in_ready[slot])
-        d2h_stream.wait_event(out_free[slot])
+        stream.wait_event(out_free[slot])            # D2H of pair i-2 has drained out_dev[slot] / out_host[slot]
         blk = sb.CorrBlock1D(f1, f2, num_levels=L, radius=r) if with_kernels else None
         for t in range(iters):
-            out = blk(c[t]) if with_kernels else scratch_out
+            if with_kernels:
+                blk(c[t], out=od[t])
             ev = torch.cuda.Event()
             ev.record(stream)
             with torch.cuda.stream(d2h_stream):
                 d2h_stream.wait_event(ev)
-                oh[t].copy_(out, non_blocking=True)
-                out.record_stream(d2h_stream)
+                oh[t].copy_(od[t], non_blocking=True)
         in_free[slot].record(stream)
         out_free[slot].record(d2h_stream)
 
@@ -781,7 +780,6 @@ def main():
             compute(i, with_kernels)
         stream.wait_stream(d2h_stream)
 
-    scratch_out = torch.empty((B, L * (2 * r + 1), H, W), dtype=torch.float32, device=dev)
     e2e_steps = max(20, min(args.steps, 200))
     with torch.set_grad_enabled(os.environ.get("BENCH_E2E_GRAD", "0") == "1"):
         run_e2e(3)
@@ -811,8 +809,9 @@ def main():
                                         "ceiling the host<->device path of this box sets at this rank count"},
            "frac_of_host_copy_ceiling": (world * e2e_steps * B / e2e_s) / (world * e2e_steps * B / copy_s),
            "host_binding": binding,
-           "how": "CorrBlock1D(...) + 32 x __call__ fed from pinned host buffers; all 32 lookup results of every "
-                  "pair copied back to pinned host memory; H2D(i+1) / compute(i) / D2H(i) pipelined on 3 streams"}
+           "how": "CorrBlock1D(...) + 32 x __call__(coords, out=staging[t]) fed from pinned host buffers; all 32 lookup "
+                  "results of every pair copied back to pinned host memory; H2D(i+1) / compute(i) / D2H(i) pipelined "
+                  "on 3 streams, double-buffered, ordered by events on the device (the host never blocks)"}
 
     # ---- eager (non-graph) API throughput, inputs resident
     with torch.no_grad():
@@ -823,7 +822,7 @@ def main():
     from smoe_stereo_b200.sharding import gather_lookup, shard_bounds
     ctx = dict(torch=torch, sb=sb, dev=dev, side=side, timer=timer, rank=rank, hbm_peak=hbm_peak, peak_src=peak_src,
                tf_peak=tf_peak, sampler=sampler, traffic=ncu_traffic, bwd_kernel="lookup_bwd_lvl_kernel<float,4>")
-    del lk_graphs, bd_graph, graphs, pin, out_host, dbuf
+    del lk_graphs, bd_graph, graphs, pin, out_host, dbuf, out_dev
     torch.cuda.empty_cache()
     configs, strong = {}, {}
     for name in extra:

@@ -329,7 +329,18 @@ def _warn_coords_grad() -> None:
                       "core/SMoEStereo.py:234 does", RuntimeWarning, stacklevel=3)
 
 
-def _lookup(pyr: FusedPyramid, coords: torch.Tensor, radius: int, out_dtype, use_ring: bool = False) -> torch.Tensor:
+def _check_out(pyr: FusedPyramid, out: torch.Tensor, radius: int, out_dtype) -> None:
+    """`out=` of CorrBlock*.__call__: the caller's own (B, L*(2r+1), H, W1) contiguous buffer."""
+    want = (pyr.B, pyr.num_levels * (2 * radius + 1), pyr.H, pyr.W1)
+    if not isinstance(out, torch.Tensor) or not out.is_cuda or out.device != pyr.device:
+        raise RuntimeError("out must be a CUDA tensor on the device of the feature maps")
+    if tuple(out.shape) != want or out.dtype is not out_dtype or not out.is_contiguous():
+        raise RuntimeError(f"out must be a contiguous {out_dtype} tensor of shape {want}, got "
+                           f"{out.dtype} {tuple(out.shape)}")
+
+
+def _lookup(pyr: FusedPyramid, coords: torch.Tensor, radius: int, out_dtype, use_ring: bool = False,
+            out: torch.Tensor | None = None) -> torch.Tensor:
     """One eager lookup.  This is the call an unmodified model makes once per GRU iteration, and its
     kernel runs ~3 us, so the host side is kept short (tools/eager_overhead.py): a contiguous fp32
     CUDA coords tensor of the right shape skips the general validation, the device switch and the
@@ -346,7 +357,9 @@ def _lookup(pyr: FusedPyramid, coords: torch.Tensor, radius: int, out_dtype, use
     else:
         coords, bstride = _coords_plane(coords, pyr.B, pyr.H, pyr.W1)
     ring = pyr.out_ring if use_ring else None
-    if ring is not None and ring[0][0].dtype is out_dtype and radius == pyr.ring_radius:
+    if out is not None:
+        _check_out(pyr, out, radius, out_dtype)
+    elif ring is not None and ring[0][0].dtype is out_dtype and radius == pyr.ring_radius:
         bufs, pos = ring
         out = bufs[pos]
         ring[1] = pos + 1 if pos + 1 < len(bufs) else 0
@@ -531,16 +544,22 @@ class _CorrBlockBase:
         p = self._state.pyr
         return [p.level(i).unsqueeze(3) for i in range(p.num_levels)]
 
-    def __call__(self, coords):
+    def __call__(self, coords, out=None):
+        """corr_fn(coords) of the reference (core/corr.py:127-146).  `out=` (an extension, optional):
+        write the result into the caller's own contiguous (B, L*(2r+1), H, W1) buffer instead of a
+        fresh tensor -- what a serving loop that stages results for a device-to-host copy wants
+        (no allocator traffic, no record_stream bookkeeping); not available while autograd records."""
         p = self._state.pyr
         out_dtype = torch.float32 if self._float_output else p.dtype
         if torch.is_grad_enabled():
             if coords.requires_grad:
                 _warn_coords_grad()
             if self._token is not None:
+                if out is not None:
+                    raise RuntimeError("out= cannot be used while autograd is recording the lookup")
                 return _LookupFn.apply(self._token, coords, self._state, out_dtype)
-            return _lookup(p, coords, self.radius, out_dtype)
-        return _lookup(p, coords, self.radius, out_dtype, True)
+            return _lookup(p, coords, self.radius, out_dtype, False, out)
+        return _lookup(p, coords, self.radius, out_dtype, True, out)
 
     def reuse_outputs(self, depth: int = 2):
         """Opt-in: serve `__call__` from a ring of `depth` preallocated output buffers instead of a

@@ -246,3 +246,31 @@ def test_optin_fp16_volume_storage(sb, oracle):
     finally:
         sb.set_default_volume_dtype(None)
     assert sb.CorrBlock1D(t1.detach(), t2)._state.pyr.dtype == torch.float32
+
+
+def test_call_with_caller_owned_output_buffer(sb):
+    """`blk(coords, out=buf)`: same bits as the allocating call, written in place; wrong shapes /
+    dtypes raise; refused while autograd records the lookup."""
+    from gpu_util import dev, make_coords
+    B, C, H, W = 2, 64, 4, 96
+    g = torch.Generator(device="cpu").manual_seed(11)
+    f1 = torch.randn((B, C, H, W), generator=g).to(dev())
+    f2 = torch.randn((B, C, H, W), generator=g).to(dev())
+    coords = torch.from_numpy(make_coords(B, H, W, W, 2, seed=2)).to(dev())
+    blk = sb.CorrBlock1D(f1, f2, num_levels=4, radius=4)
+    staging = torch.full((2, B, 36, H, W), float("nan"), device=dev())
+    with torch.no_grad():
+        for t in range(2):
+            want = blk(coords[t])
+            got = blk(coords[t], out=staging[t])
+            assert got.data_ptr() == staging[t].data_ptr()
+            assert torch.equal(got, want)
+        with pytest.raises(RuntimeError):
+            blk(coords[0], out=staging[0, :, :35])
+        with pytest.raises(RuntimeError):
+            blk(coords[0], out=staging[0].half())
+        with pytest.raises(RuntimeError):
+            blk(coords[0], out=staging[0].cpu())
+    tr = sb.CorrBlock1D(f1.clone().requires_grad_(True), f2, num_levels=4, radius=4)
+    with pytest.raises(RuntimeError):
+        tr(coords[0], out=staging[0])
