@@ -809,8 +809,11 @@ lookup_bwd_tma_kernel(const __grid_constant__ BwdBatch batch, const __grid_const
   constexpr int R = 4, RD = 9, NC = NL * RD, ROWS = NC + 1, S = kTmaStages;
   extern __shared__ __align__(16) uint8_t s_raw[];
   __shared__ __align__(8) uint64_t s_full[S], s_empty[S];
-  // TMA tensor loads want 128-byte aligned destinations: align the dynamic part by hand
-  float* s_t = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(s_raw) + 127) & ~(uintptr_t)127);   // [geo.rowlen columns][kTilePx]
+  // TMA tensor loads want 128-byte aligned destinations: align the dynamic part by hand -- on the
+  // 32-bit shared-window address, so that every pointer below is still provably a shared-memory
+  // pointer (rounding the generic address up through uintptr_t made ptxas emit generic LD/ST with
+  // 64-bit address arithmetic for every tile access: 200 instructions per iteration instead of 110)
+  float* s_t = reinterpret_cast<float*>(s_raw + ((128u - (ptx_smem(s_raw) & 127u)) & 127u));   // [geo.rowlen columns][kTilePx]
   float* s_ring = s_t + geo.rowlen * kTilePx;                         // [S][ROWS][kTilePx]; later staging
 
   pdl_launch_dependents();
@@ -834,11 +837,10 @@ lookup_bwd_tma_kernel(const __grid_constant__ BwdBatch batch, const __grid_const
   }
   __syncthreads();
 
-  auto produce = [&](int t) {                         // one lane of the producer warp
+  auto produce = [&](int t, int slot) {               // one lane of the producer warp
     if (lane == 0) {
-      const int slot = t % S;
       const uint32_t bar = ptx_smem(&s_full[slot]);
-      const uint32_t dst = ptx_smem(s_ring + (long long)slot * ROWS * kTilePx);
+      const uint32_t dst = ptx_smem(s_ring + slot * (ROWS * kTilePx));
       mbar_expect_tx_(bar, NC * kTilePx * 4 + row_bytes);          // the box counts in full, tails included
       ptx::tma_load_3d(dst, &maps.gout[t], bar, hw0, 0, b);
       bulk_copy_g2s(dst + NC * kTilePx * 4, batch.coords[t] + (long long)b * batch.coords_bstride[t] + hw0,
@@ -846,7 +848,7 @@ lookup_bwd_tma_kernel(const __grid_constant__ BwdBatch batch, const __grid_const
     }
   };
   if (warp == 4) {
-    for (int t = 0; t < S && t < T; ++t) produce(t);  // the stream starts before the tile is cleared
+    for (int t = 0; t < S && t < T; ++t) produce(t, t);   // the stream starts before the tile is cleared
   }
   for (int i = tid; i < geo.rowlen * (kTilePx / 4); i += 160)
     reinterpret_cast<float4*>(s_t)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -860,36 +862,54 @@ lookup_bwd_tma_kernel(const __grid_constant__ BwdBatch batch, const __grid_const
   __syncthreads();
 
   if (warp == 4) {
+    int slot = 0;
+    uint32_t parity = 0;                               // parity of the slot's previous release
     for (int t = S; t < T; ++t) {
-      mbar_wait_(ptx_smem(&s_empty[t % S]), (uint32_t)((t / S) - 1) & 1u);
-      produce(t);
+      mbar_wait_(ptx_smem(&s_empty[slot]), parity);
+      produce(t, slot);
+      if (++slot == S) { slot = 0; parity ^= 1u; }
     }
   } else if (warp < NL) {
     const int l = warp;
     float* coll = s_t + geo.off[l] * kTilePx + lane;
-    const unsigned width = (unsigned)geo.width[l];
+    const int width = geo.width[l];
     const float lscale = 1.0f / (float)(1 << l);
     const bool worker = lane < npx;
+    int slot = 0;
+    uint32_t parity = 0;
     for (int t = 0; t < T; ++t) {
-      const int slot = t % S;
-      mbar_wait_(ptx_smem(&s_full[slot]), (uint32_t)(t / S) & 1u);
-      const float* src = s_ring + ((long long)slot * ROWS) * kTilePx + lane;
-      float gt[RD], xt = 0.f;
+      mbar_wait_(ptx_smem(&s_full[slot]), parity);
+      const float* src = s_ring + slot * (ROWS * kTilePx) + l * (RD * kTilePx) + lane;
+      float gt[RD];
 #pragma unroll
-      for (int k = 0; k < RD; ++k) gt[k] = worker ? src[(l * RD + k) * kTilePx] : 0.f;
-      if (worker) xt = src[NC * kTilePx];
+      for (int k = 0; k < RD; ++k) gt[k] = src[k * kTilePx];           // (idle lanes of a tail tile read zero-filled columns)
+      const float xt = s_ring[slot * (ROWS * kTilePx) + NC * kTilePx + (worker ? lane : 0)];
       __syncwarp();
       if (lane == 0) mbar_arrive_(ptx_smem(&s_empty[slot]));       // this warp is done with the stage
-      if (worker) {
-        int base;
-        float dx;
-        split_coord(xt * lscale, R, base, dx);
-        float* win = coll + base * kTilePx;
+      if (++slot == S) { slot = 0; parity ^= 1u; }
+      int base;
+      float dx;
+      split_coord(xt * lscale, R, base, dx);
+      float* win = coll + base * kTilePx;
+      // the whole window inside the row for every pixel of the warp (the common case): no per-tap predicates
+      const bool inside = base >= 0 && base + RD < width;
+      if (__all_sync(0xffffffffu, inside || !worker)) {
+        if (worker) {
+          float cur[RD + 1];
+#pragma unroll
+          for (int k = 0; k <= RD; ++k) cur[k] = win[k * kTilePx];
+#pragma unroll
+          for (int k = 0; k <= RD; ++k)
+            cur[k] += BwdTap<float>::eval(k > 0 ? gt[k - 1] : 0.f, k < RD ? gt[k] : 0.f, k > 0, k < RD, dx);
+#pragma unroll
+          for (int k = 0; k <= RD; ++k) win[k * kTilePx] = cur[k];
+        }
+      } else if (worker) {
         float cur[RD + 1];
         bool ok[RD + 1];
 #pragma unroll
         for (int k = 0; k <= RD; ++k) {
-          ok[k] = (unsigned)(base + k) < width;
+          ok[k] = (unsigned)(base + k) < (unsigned)width;
           cur[k] = ok[k] ? win[k * kTilePx] : 0.f;
         }
 #pragma unroll
