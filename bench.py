@@ -821,7 +821,7 @@ def main():
     # ---- BASELINE configs 2-5 (N=1: whole configs; N>1: this rank's shard = strong scaling)
     from smoe_stereo_b200.sharding import gather_lookup, shard_bounds
     ctx = dict(torch=torch, sb=sb, dev=dev, side=side, timer=timer, rank=rank, hbm_peak=hbm_peak, peak_src=peak_src,
-               tf_peak=tf_peak, sampler=sampler, traffic=ncu_traffic, bwd_kernel="lookup_bwd_lvl_kernel<float,4>")
+               tf_peak=tf_peak, sampler=sampler, traffic=ncu_traffic, bwd_kernel="lookup_bwd_tma_kernel<4>")
     del lk_graphs, bd_graph, graphs, pin, out_host, dbuf, out_dev
     torch.cuda.empty_cache()
     configs, strong = {}, {}

@@ -775,6 +775,15 @@ lookup_bwd_async_kernel(const __grid_constant__ BwdBatch batch, const BatchedGeo
 // write-out folds 4 columns at a time with lane = pixel, transposes 32x32 blocks through a padded
 // staging tile (carved out of the ring, idle by then) and stores whole 128-byte row segments.
 // Same arithmetic and accumulation order per element as every other version => bit-identical.
+// Measured at BASELINE config 2 (profiles/r02/bwd_variants*.log, ncu in profiles/r02): 108 us vs 155 us
+// for lookup_bwd_lvl_kernel (DRAM floor 72 us).  ncu: L1/shared data pipe 65 % busy (per tile: ring
+// fill 814 + ring reads 880 + window read-modify-write 1760 + clear 345 + fold 345 + stores ~570
+// wavefronts), DRAM 48 %, issue 50 %: the shared-memory pipe is the soft limit, every access queues.
+// Variants that moved the same wavefronts measured no better: persistent CTAs with the producer
+// running across tile boundaries (111), guard columns instead of per-tap predicates + a software
+// pipeline over the ring (113), a register queue of 2-6 stages on top of the ring (117-124), two
+// warps per level (115-123), L2 prefetch 8-32 stages ahead (122-142), helper warps for the clear /
+// fold / write phases (117-120), shallower rings with four CTAs per SM (136).
 constexpr int kTmaStages = 6;
 __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -1080,7 +1089,8 @@ static int fwd_kernel_choice() { return 0; }
 constexpr bool kXcheck = false;
 #endif
 constexpr int kStreamPxHint = 5;         // volumes >> L2: level-0 fills and output stores evict_first
-constexpr int kDefaultBwdKernel = 1;     // Tuning::bwd_kernel: 1 = lookup_bwd_lvl_kernel, 2 = lookup_bwd_cp_kernel
+constexpr int kDefaultBwdKernel = 4;     // Tuning::bwd_kernel: 1 = lookup_bwd_lvl_kernel, 2 = lookup_bwd_cp_kernel, 3 = async,
+                                         // 4 = lookup_bwd_tma_kernel (fp32 gradients, 16-byte aligned planes; else falls back to 2)
 
 // The 256-bit path reads whole 32-byte chunks aligned in MEMORY: the first chunk of a level may
 // begin 16 bytes before the level and the last may end 16 bytes after its row.  That stays inside
