@@ -76,6 +76,14 @@ __device__ __forceinline__ void st_hint(__half* p, __half v, unsigned long long 
   asm volatile("st.global.L2::cache_hint.b16 [%0], %1, %2;" ::"l"(p), "h"(__half_as_ushort(v)), "l"(pol) : "memory");
 }
 
+// Measured and rejected in round 2 (profiles/r02/lookup_loop_variant_*.log): the streaming lookup as
+// PERSISTENT CTAs that walk their tiles in a grid-stride loop with the next tile's coordinate in
+// flight (k tiles = 1 + k dependent DRAM round trips instead of 2k).  Slower at every streaming
+// config (cfg2 8.4 -> 10.1 us, cfg3 17.9 -> 20.0 us, cfg4 33.4 -> 37.5 us at 64 registers; worse at
+// 128): the hardware's CTA scheduler already overlaps the two phases across the 16 small CTAs an
+// SM holds.  In steady state (32 lookups back to back) the kernel moves 59.6 MB of DRAM reads (64-byte
+// fills around 80-byte segments; 39 MB useful) + 34.5 MB of output per config-3 launch in 17.9 us =
+// 5.3 TB/s, 80 % of the measured copy peak: it is DRAM-bound on the bytes the fill granularity forces.
 template <typename VT, typename OT, int R, int NL, bool STREAM, bool SPLIT, bool LD256 = false, int HINT = 0>
 __global__ void __launch_bounds__(256)
 lookup_fwd_px_kernel(PyrDev pyr, const float* __restrict__ coords, long long coords_bstride,
