@@ -1,0 +1,94 @@
+"""gpurun_out/prof2/* (tools/collect_profiles_r02.sh) -> tracked summaries under profiles/r02/:
+launch list + per-kernel share of the bench command, one metric table per (kernel class, config)
+capture, traffic.json (dram bytes per launch, read by bench.py for roofline.traffic)."""
+import collections
+import csv
+import json
+import os
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "gpurun_out", "prof2")
+DST = os.path.join(ROOT, "profiles", "r02")
+os.makedirs(DST, exist_ok=True)
+
+
+def launch_summary():
+    rows = [r for r in csv.reader(l for l in open(os.path.join(SRC, "launches.csv")) if l.startswith('"'))]
+    hdr = rows[0]
+    kn, mv, unit = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    tot = collections.OrderedDict()
+    for r in rows[1:]:
+        v = float(r[mv].replace(",", ""))
+        v = v / 1e3 if r[unit] in ("ns", "nsecond") else v
+        t = tot.setdefault(r[kn], [0.0, 0])
+        t[0] += v
+        t[1] += 1
+    s = sum(t[0] for t in tot.values())
+    with open(os.path.join(DST, "launches_bench_summary.txt"), "w") as f:
+        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none of `python bench.py --steps 2 --warmup 3 "
+                "--no-cpu-baseline --configs cfg2,cfg3` (cold-cache, serialised replays: shares, not absolutes)\n")
+        for k, (v, n) in sorted(tot.items(), key=lambda kv: -kv[1][0]):
+            f.write(f"{v:10.1f} us {100*v/s:5.1f}%  n={n:4d} avg={v/n:8.2f} us  {k[:110]}\n")
+    # the full per-launch list is 700 KB: keep the first 400 launches (warm-up + timed cfg1 steps) verbatim
+    with open(os.path.join(SRC, "launches.csv")) as f, open(os.path.join(DST, "launches_bench_head.csv"), "w") as g:
+        n = 0
+        for line in f:
+            if line.startswith('"'):
+                n += 1
+            if n > 401:
+                break
+            g.write(line)
+
+
+def metrics(rep, out):
+    txt = subprocess.run([sys.executable, os.path.join(ROOT, "profiles", "ncu_metrics.py"), os.path.join(SRC, rep)],
+                         capture_output=True, text=True).stdout
+    open(os.path.join(DST, out), "w").write(txt)
+    vals = {}
+    for line in txt.splitlines():
+        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum"):
+            if line.startswith(key + " "):
+                unit = line.split()[1]
+                first = float(line.split("[")[1].split(",")[0].strip("' ]"))
+                mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "us": 1, "ns": 1e-3, "ms": 1e3}.get(unit, 1)
+                vals[key] = first * mult
+        if line.startswith("kernels:"):
+            vals["kernel"] = line
+    return vals
+
+
+CAPTURES = [   # file stem, traffic.json key (the instantiation bench.py names), note
+    ("build_cfg1", "corr_build_kernel<float,float,false,false>@cfg1"),
+    ("build_cfg2", "corr_build_kernel<float,float,false,false>@cfg2"),
+    ("build_cfg3", "corr_build_kernel<float,float,false,false>@cfg3"),
+    ("lookup_cfg1", "lookup_fwd_px_kernel<float,float,4,4,false,true,false,0>@cfg1"),
+    ("lookup_cfg2", "lookup_fwd_px_kernel<float,float,4,4,true,true,true,0>@cfg2"),
+    ("lookup_cfg3", "lookup_fwd_px_kernel<float,float,4,4,true,true,true,5>@cfg3"),
+    ("lookup_cfg4", "lookup_fwd_px_kernel<float,float,4,4,true,true,true,5>@cfg4"),
+    ("lookup_bwd_cfg2", "lookup_bwd_batched@cfg2"),
+    ("build_bwd_cfg2", "corr_build_bwd_kernel@cfg2"),
+]
+
+if __name__ == "__main__":
+    launch_summary()
+    t = {"_note": "dram__bytes_read.sum / dram__bytes_write.sum of ONE launch from the ncu --set full captures in this "
+                  "directory (tools/collect_profiles_r02.sh: eager launches through the product library, cold-ish "
+                  "cache, serialised).  Writes still in L2 when the kernel ends are not in dram__bytes_write; bench.py "
+                  "adds read + write as roofline.traffic and says so."}
+    for stem, key in CAPTURES:
+        rep = stem + ".ncu-rep"
+        if not os.path.exists(os.path.join(SRC, rep)):
+            continue
+        v = metrics(rep, f"ncu_{stem}.txt")
+        t[key] = {"read": int(v["dram__bytes_read.sum"]), "write": int(v["dram__bytes_write.sum"]),
+                  "ncu_duration_us": v["gpu__time_duration.sum"], "source": f"ncu_{stem}.txt",
+                  "kernel_in_capture": v.get("kernel", "")[:160]}
+    json.dump(t, open(os.path.join(DST, "traffic.json"), "w"), indent=2)
+    for f in ("bench_plain.log",):
+        if os.path.exists(os.path.join(SRC, f)):
+            shutil.copy(os.path.join(SRC, f), os.path.join(DST, "bench_under_collect_" + f))
+    print(open(os.path.join(DST, "launches_bench_summary.txt")).read())
+    print(json.dumps(t, indent=1))
