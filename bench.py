@@ -543,9 +543,16 @@ def measure_cfg5(ctx, frames=3):
         t_ours, d_ours = timed()
     finally:
         sb.uninstall()
+    sb.install(output_ring=2)          # opt-in: lookups served from a two-buffer ring
+    try:
+        t_ring, d_ring = timed()
+    finally:
+        sb.uninstall()
     res = {"workload": "SMoEStereo damv2/vitl + SMoE PEFT (unmodified reference model, random init), 544x960, B=1, "
                        "32 iterations, mixed_precision=True, corr_implementation=reg",
            "frames_per_s": 1.0 / t_ours, "frames_per_s_stock_corr_on_gpu": 1.0 / t_stock,
+           "frames_per_s_install_output_ring_2": 1.0 / t_ring,
+           "output_ring_equals_default": bool(torch.equal(d_ring, d_ours)),
            "ms_per_frame": 1e3 * t_ours, "ms_per_frame_stock_corr_on_gpu": 1e3 * t_stock,
            "epe_px_vs_stock": (d_ours - d_stock).abs().mean().item(), "frames_timed": frames,
            "how": "wall clock around model(left, right, iters=32, test_mode=True) + synchronize, eager PyTorch; "
@@ -633,13 +640,17 @@ def main():
                      torch.from_numpy(coords).to(dev)))
     torch.cuda.synchronize()
 
+    # per-iteration coordinate tensors, as a model has them (slicing a stacked tensor costs ~2 us of host
+    # time per call, two thirds of a lookup kernel)
+    coord_lists = {id(s[2]): list(s[2].unbind(0)) for s in sets}
+
     def step_eager(f1, f2, coords, ring=0):
         blk = sb.CorrBlock1D(f1, f2, num_levels=L, radius=r)
         if ring:
             blk.reuse_outputs(ring)
         out = None
-        for t in range(iters):
-            out = blk(coords[t])
+        for c in coord_lists[id(coords)]:
+            out = blk(c)
         return blk, out
 
     side = torch.cuda.Stream(dev)

@@ -7,7 +7,8 @@ plus ``install()`` to make them the implementations an unmodified reference chec
 from . import _lib                                             # noqa: F401
 from . import corr_sampler                                     # noqa: F401
 from .corr import (AlternateCorrBlock, CorrBlock1D, CorrBlockFast1D, CorrSampler,  # noqa: F401
-                   FusedPyramid, PytorchAlternateCorrBlock1D, set_default_volume_dtype)
+                   FusedPyramid, PytorchAlternateCorrBlock1D, set_default_output_ring,
+                   set_default_volume_dtype)
 from .dropin import install, uninstall                        # noqa: F401
 from .sharding import shard_bounds, gather_lookup, ShardedCorrBlock1D   # noqa: F401
 

@@ -30,7 +30,7 @@ from . import _lib
 from . import corr_sampler
 
 __all__ = ["CorrBlock1D", "CorrBlockFast1D", "PytorchAlternateCorrBlock1D", "CorrSampler",
-           "AlternateCorrBlock"]
+           "AlternateCorrBlock", "set_default_output_ring", "set_default_volume_dtype"]
 
 _DTYPE_CODE = {torch.float32: _lib.DTYPE_F32, torch.float16: _lib.DTYPE_F16}
 
@@ -47,6 +47,19 @@ _default_volume_dtype = torch.float16 if os.environ.get("SMOE_CORR_VOLUME_DTYPE"
 # radius-4 blocks (the default, see _CorrBlockBase.__init__)
 _skip_odd_levels = {"": None, "0": True, "1": False}.get(os.environ.get("SMOE_CORR_ALL_LEVELS", ""), None)
 _SKIP_ODD_MIN_BYTES = 0             # None above: skip levels 1/3 for volumes of at least this size
+
+
+# Opt-in (set_default_output_ring / install(output_ring=n)): every block serves its no-grad lookups from
+# a ring of n preallocated output buffers (see _CorrBlockBase.reuse_outputs).  0 = a fresh tensor per call.
+_default_output_ring = 0
+
+
+def set_default_output_ring(depth: int) -> None:
+    """depth > 0: blocks constructed from now on call reuse_outputs(depth) on themselves -- for update
+    loops that consume `corr` inside the iteration that produced it (core/raft_stereo.py:205-214,
+    core/SMoEStereo.py:233-248).  Only affects calls made while autograd is not recording."""
+    global _default_output_ring
+    _default_output_ring = max(int(depth), 0)
 
 
 def set_default_volume_dtype(dtype) -> None:
@@ -129,6 +142,9 @@ class FusedPyramid:
         # cached for the eager per-call path (_lookup): device ordinal, coords plane geometry
         self.dev_idx = device.index if device.index is not None else _raw_device()
         self._coords_fast = (H * W1, W1, 1)          # strides (ch, H, W) of a contiguous coords tensor
+        # (shape, stride) of the contiguous 2- and 1-channel coords tensors the models pass -> batch stride
+        self._coords_ok = {(torch.Size((B, c, H, W1)), (c * H * W1, H * W1, W1, 1)): c * H * W1 for c in (1, 2)}
+        self._out_shape = {}
 
     def level(self, i: int) -> torch.Tensor:
         """Strided (B,H,W1,W2_i) view of level i (no copy)."""
@@ -349,13 +365,16 @@ def _lookup(pyr: FusedPyramid, coords: torch.Tensor, radius: int, out_dtype, use
     global _lookup_fn
     if _lookup_fn is None:
         _lookup_fn = _lib.fast_lookup()
-    shp = coords.shape
-    if (coords.dtype is torch.float32 and coords.is_cuda and len(shp) == 4 and shp[0] == pyr.B
-            and shp[2] == pyr.H and shp[3] == pyr.W1 and coords.stride()[1:] == pyr._coords_fast
-            and (pyr.B == 1 or coords.stride(0) >= pyr._coords_fast[0])):
-        bstride = coords.stride(0) if pyr.B > 1 else shp[1] * pyr._coords_fast[0]
-    else:
-        coords, bstride = _coords_plane(coords, pyr.B, pyr.H, pyr.W1)
+    # fast path: a contiguous fp32 CUDA (B, 1|2, H, W1) tensor -- one tuple comparison per property
+    bstride = pyr._coords_ok.get((coords.shape, coords.stride())) if coords.dtype is torch.float32 and coords.is_cuda else None
+    if bstride is None:
+        shp = coords.shape
+        if (coords.dtype is torch.float32 and coords.is_cuda and len(shp) == 4 and shp[0] == pyr.B
+                and shp[2] == pyr.H and shp[3] == pyr.W1 and coords.stride()[1:] == pyr._coords_fast
+                and (pyr.B == 1 or coords.stride(0) >= pyr._coords_fast[0])):
+            bstride = coords.stride(0) if pyr.B > 1 else shp[1] * pyr._coords_fast[0]
+        else:
+            coords, bstride = _coords_plane(coords, pyr.B, pyr.H, pyr.W1)
     ring = pyr.out_ring if use_ring else None
     if out is not None:
         _check_out(pyr, out, radius, out_dtype)
@@ -364,8 +383,10 @@ def _lookup(pyr: FusedPyramid, coords: torch.Tensor, radius: int, out_dtype, use
         out = bufs[pos]
         ring[1] = pos + 1 if pos + 1 < len(bufs) else 0
     else:
-        out = torch.empty((pyr.B, pyr.num_levels * (2 * radius + 1), pyr.H, pyr.W1), dtype=out_dtype,
-                          device=pyr.device)
+        shape = pyr._out_shape.get(radius)
+        if shape is None:
+            shape = pyr._out_shape[radius] = (pyr.B, pyr.num_levels * (2 * radius + 1), pyr.H, pyr.W1)
+        out = torch.empty(shape, dtype=out_dtype, device=pyr.device)
     idx = pyr.dev_idx
     if _raw_stream is not None and _raw_device() == idx:
         rc = _lookup_fn(pyr.addr, coords.data_ptr(), bstride, radius, out.data_ptr(),
@@ -537,6 +558,8 @@ class _CorrBlockBase:
             st.pyr = FusedPyramid(fmap1.shape[0], fmap1.shape[2], fmap1.shape[3], fmap2.shape[3],
                                   num_levels, pyr_dtype, fmap1.device)
             _build_into(st.pyr, fmap1, fmap2, st.build_flags)
+            if _default_output_ring:
+                self.reuse_outputs(_default_output_ring)
 
     @property
     def corr_pyramid(self):

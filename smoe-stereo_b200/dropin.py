@@ -21,9 +21,14 @@ _saved: dict = {}
 _ABSENT = object()
 
 
-def install(modules=_TARGETS) -> list[str]:
-    """Returns the list of 'module.name' bindings that were replaced."""
+def install(modules=_TARGETS, output_ring: int = 0) -> list[str]:
+    """Returns the list of 'module.name' bindings that were replaced.
+
+    output_ring > 0 (opt-in): inference lookups are served from a ring of that many preallocated
+    output buffers per block instead of a fresh tensor per call (corr.set_default_output_ring) --
+    valid for the reference's update loops, which consume `corr` inside the iteration."""
     replaced = []
+    _corr.set_default_output_ring(output_ring)
     if sys.modules.get("corr_sampler") is not _sampler:
         _saved[("sys.modules", "corr_sampler")] = sys.modules.get("corr_sampler")
         sys.modules["corr_sampler"] = _sampler
@@ -48,6 +53,7 @@ def install(modules=_TARGETS) -> list[str]:
 
 
 def uninstall() -> None:
+    _corr.set_default_output_ring(0)
     for (mname, n), old in list(_saved.items()):
         if mname == "sys.modules":
             if old is None:

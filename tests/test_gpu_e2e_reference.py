@@ -132,3 +132,26 @@ def test_smoestereo_vitl_32_iterations_epe(smoe_fp32, impl):
     print(f"\n[e2e SMoEStereo vitl {impl} vs stock {stock_impl}] mean|disp| {r['disp']:.3f} px  EPE {r['epe']:.3e} px "
           f"(max {r['epe_max']:.3e}; stock run-to-run {r['floor']:.1e})")
     assert r["epe"] <= EPE_TOL
+
+
+def test_install_with_output_ring_gives_identical_disparities(raft_fp32):
+    """install(output_ring=2): the update loop of the reference consumes `corr` inside the iteration
+    (core/raft_stereo.py:205-214), so serving lookups from a two-buffer ring changes nothing."""
+    import smoe_stereo_b200 as sb
+    model, left, right = raft_fp32
+    model.args.corr_implementation = "reg"
+    sb.uninstall()
+    sb.install()
+    try:
+        a = _disp(model, left, right, 12)
+    finally:
+        sb.uninstall()
+    sb.install(output_ring=2)
+    try:
+        import smoe_stereo_b200.corr as c
+        assert c._default_output_ring == 2
+        b = _disp(model, left, right, 12)
+    finally:
+        sb.uninstall()
+    assert c._default_output_ring == 0
+    assert torch.equal(a, b)
