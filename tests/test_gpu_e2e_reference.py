@@ -155,3 +155,37 @@ def test_install_with_output_ring_gives_identical_disparities(raft_fp32):
         sb.uninstall()
     assert c._default_output_ring == 0
     assert torch.equal(a, b)
+
+
+def test_channels_last_producer_feeds_the_build_in_place(raft_fp32):
+    """SURVEY.md 8f row f4 with a REAL producer: the reference model run in
+    memory_format=torch.channels_last makes cuDNN emit (B,H,W,C) feature maps; the drop-in hands
+    them to the build kernel as they are (K-major operands, no .contiguous() copy) and the
+    32-iteration disparity stays within the north_star tolerance of the stock NCHW run."""
+    import smoe_stereo_b200 as sb
+    import smoe_stereo_b200.corr as c
+    model, left, right = raft_fp32
+    model.args.corr_implementation = "reg"
+    sb.uninstall()
+    stock = _disp(model, left, right, 32)
+    seen = []
+    real_build = c._build_into
+
+    def spy(pyr, f1, f2, flags=0):
+        seen.append((c._is_channels_last(f1), c._is_channels_last(f2), f1.data_ptr()))
+        return real_build(pyr, f1, f2, flags)
+
+    model.to(memory_format=torch.channels_last)
+    c._build_into = spy
+    sb.install()
+    try:
+        ours = _disp(model, left.contiguous(memory_format=torch.channels_last),
+                     right.contiguous(memory_format=torch.channels_last), 32)
+    finally:
+        sb.uninstall()
+        c._build_into = real_build
+        model.to(memory_format=torch.contiguous_format)
+    assert seen and all(a and b for a, b, _ in seen), f"the producer did not emit channels-last features: {seen}"
+    epe = (stock - ours).abs().mean().item()
+    print(f"\n[e2e RAFTStereo channels-last producer] EPE vs stock NCHW {epe:.3e} px")
+    assert epe <= EPE_TOL
