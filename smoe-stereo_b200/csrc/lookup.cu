@@ -512,10 +512,13 @@ template <int N> __device__ __forceinline__ void cp_async_wait_group() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// PF: software L2 prefetch of the gradient / coordinate lines PF iterations ahead (prefetch.global.L2: no
+// register, no scoreboard).  cfg2 fp32: 141 -> 120 us with PF = 2 (4: 122, 8: 126); the product uses
+// PF = 2 where this kernel is its path (fp16 gradients, planes that are not 16-byte aligned).
 // PROBE (cross-check builds, tools/variants_probe.py): 1 = stream the gradients but do not scatter
 // (what the global loads alone cost), 2 = scatter constants without loading anything (what the
 // shared-memory work alone costs).  0 = the real kernel.
-template <typename GT, int NL, int PROBE = 0>
+template <typename GT, int NL, int PROBE = 0, int PF = 0>
 __global__ void __launch_bounds__(128)
 lookup_bwd_cp_kernel(const __grid_constant__ BwdBatch batch, const BatchedGeom geo,
                      float* __restrict__ g0_out, long long g0_pitch, int HW, int accumulate) {
@@ -550,7 +553,17 @@ lookup_bwd_cp_kernel(const __grid_constant__ BwdBatch batch, const BatchedGeom g
     const long long gofs = ((long long)b * NC + l * RD) * HW + hw0 + lane;
     float g[kDepth][RD], x[kDepth];
     float probe_acc = 0.f;
+    // PF > 0: ask L2 for the lines of iteration t + PF (fire and forget: no register, no scoreboard)
+    auto prefetch = [&](int t) {
+      if (PF > 0 && t < batch.T) {
+        const GT* gp = static_cast<const GT*>(batch.gout[t]) + gofs;
+#pragma unroll
+        for (int k = 0; k < RD; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(gp + (long long)k * HW));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(batch.coords[t] + (long long)b * batch.coords_bstride[t] + hw0 + lane));
+      }
+    };
     auto load = [&](int t, float (&gt)[RD], float& xt) {
+      prefetch(t + PF);
       if (PROBE == 2) {
 #pragma unroll
         for (int k = 0; k < RD; ++k) gt[k] = 0.25f * (float)(k + t);
@@ -588,6 +601,9 @@ lookup_bwd_cp_kernel(const __grid_constant__ BwdBatch batch, const BatchedGeom g
         if (ok[k]) win[k * kTilePx] = cur[k];
     };
     const int T = batch.T;
+    if (PF > 0) {
+      for (int t = kDepth - 1; t < kDepth - 1 + PF; ++t) prefetch(t);
+    }
 #pragma unroll
     for (int u = 0; u < kDepth - 1; ++u)
       if (u < T) load(u, g[u], x[u]);
@@ -1525,6 +1541,10 @@ int smoe_corr_lookup_bwd_batched(const smoe_pyramid_t* g0, int num_levels, int n
     else if (tma) SMOE_LAUNCH_TMA(NLV);                                                                  \
     else if (which == 11) SMOE_LAUNCH_FN((lookup_bwd_cp_kernel<GT, NLV, 1>), 128);                       \
     else if (which == 12) SMOE_LAUNCH_FN((lookup_bwd_cp_kernel<GT, NLV, 2>), 128);                       \
+    else if (which == 21) SMOE_LAUNCH_FN((lookup_bwd_cp_kernel<GT, NLV, 0, 2>), 128);                    \
+    else if (which == 22) SMOE_LAUNCH_FN((lookup_bwd_cp_kernel<GT, NLV, 0, 4>), 128);                    \
+    else if (which == 23) SMOE_LAUNCH_FN((lookup_bwd_cp_kernel<GT, NLV, 0, 8>), 128);                    \
+    else if (which == 24) SMOE_LAUNCH_FN((lookup_bwd_cp_kernel<GT, NLV, 1, 4>), 128);                    \
     else if (which >= 2) SMOE_LAUNCH_KERN(lookup_bwd_cp_kernel, GT, NLV, 128);                           \
     else SMOE_LAUNCH_KERN(lookup_bwd_lvl_kernel, GT, NLV, 128);                                          \
   } while (0)
@@ -1533,7 +1553,7 @@ int smoe_corr_lookup_bwd_batched(const smoe_pyramid_t* g0, int num_levels, int n
   do {                                                                                                   \
     if (async) SMOE_LAUNCH_ASYNC(NLV);                                                                   \
     else if (tma) SMOE_LAUNCH_TMA(NLV);                                                                  \
-    else if (kDefaultBwdKernel >= 2) SMOE_LAUNCH_KERN(lookup_bwd_cp_kernel, GT, NLV, 128);               \
+    else if (kDefaultBwdKernel >= 2) SMOE_LAUNCH_FN((lookup_bwd_cp_kernel<GT, NLV, 0, 2>), 128);         \
     else SMOE_LAUNCH_KERN(lookup_bwd_lvl_kernel, GT, NLV, 128);                                          \
   } while (0)
 #endif

@@ -66,6 +66,8 @@ def probe_bwd(L):
     for which, name in ((1, "lvl   [pixel][column], register ring"), (2, "cp    [column][pixel], register ring"),
                         (3, "async [column][pixel], cp.async ring  "),
                         (4, "tma   [column][pixel], TMA producer   "),
+                        (21, "cp + L2 prefetch 2 iterations ahead  "), (22, "cp + L2 prefetch 4 iterations ahead  "),
+                        (23, "cp + L2 prefetch 8 iterations ahead  "), (24, "PROBE cp+pf4: gradient loads only    "),
                         (11, "PROBE cp: gradient loads only        "), (12, "PROBE cp: scatter + fold only        ")):
         L.smoe_corr_debug_set_tuning(b"bwd_kernel", which)
         hold = {}
@@ -77,7 +79,7 @@ def probe_bwd(L):
         out = hold["g"].level(0).clone()
         if ref is None:
             ref = out
-        if which > 10:
+        if which in (11, 12, 24):
             out = ref
         print(f"bwd cfg2 {name}: {us:7.1f} us  ({floor_mb / us:6.2f} TB/s on the {floor_mb:.0f} MB DRAM floor, "
               f"{floor_mb / us / PEAK * 1e3 * 100:4.1f}% of peak)  bit-identical to lvl: {torch.equal(out, ref)}", flush=True)
