@@ -807,7 +807,8 @@ lookup_bwd_async_kernel(const __grid_constant__ BwdBatch batch, const BatchedGeo
 // running across tile boundaries (111), guard columns instead of per-tap predicates + a software
 // pipeline over the ring (113), a register queue of 2-6 stages on top of the ring (117-124), two
 // warps per level (115-123), L2 prefetch 8-32 stages ahead (122-142), helper warps for the clear /
-// fold / write phases (117-120), shallower rings with four CTAs per SM (136).
+// fold / write phases (117-120), shallower rings with four CTAs per SM (136), L2 prefetch by the idle
+// lanes of the producer warp 2 / 4 / 8 stages ahead (109 / 109 / 123; profiles/r02/bwd_variants_tma_l2_prefetch.log).
 constexpr int kTmaStages = 6;
 __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
