@@ -323,3 +323,54 @@ def test_gru_loop_captured_in_a_cuda_graph(sb):
             torch.cuda.synchronize()
             for a, b in zip(got, want):
                 assert torch.equal(a, b)
+
+
+def test_concurrent_host_threads_and_streams_on_one_device(sb):
+    """Re-entrancy on ONE GPU (what the driver's single-GPU box can run): four host threads, each with
+    its own CUDA stream, build blocks of different shapes, look up and back-propagate concurrently;
+    every thread must get exactly what it gets when it runs alone (no global mutable state in the
+    library, thread-local error strings, kernels on the caller's current stream)."""
+    import threading
+    from gpu_util import dev, make_coords
+    shapes = [(1, 64, 4, 64), (2, 32, 5, 96), (1, 128, 3, 40), (2, 64, 6, 37)]
+    cases = []
+    for i, (B, C, H, W) in enumerate(shapes):
+        g = torch.Generator(device="cpu").manual_seed(100 + i)
+        f1 = torch.randn(B, C, H, W, generator=g).to(dev())
+        f2 = torch.randn(B, C, H, W, generator=g).to(dev())
+        coords = torch.from_numpy(make_coords(B, H, W, W, 3, seed=i)).to(dev())
+        cases.append((f1, f2, coords))
+
+    def run(case):
+        f1, f2, coords = case
+        a = f1.clone().requires_grad_(True)
+        blk = sb.CorrBlock1D(a, f2, num_levels=4, radius=4)
+        outs = [blk(coords[t]) for t in range(3)]
+        sum(o.square().sum() for o in outs).backward()
+        return [o.detach().clone() for o in outs], a.grad.clone()
+
+    alone = [run(c) for c in cases]
+    torch.cuda.synchronize()
+    results, errors = {}, []
+
+    def worker(i):
+        try:
+            s = torch.cuda.Stream(dev())
+            with torch.cuda.device(dev()), torch.cuda.stream(s):
+                for _ in range(10):
+                    results[i] = run(cases[i])
+                s.synchronize()
+        except Exception as e:          # noqa: BLE001
+            errors.append((i, repr(e)))
+
+    th = [threading.Thread(target=worker, args=(i,)) for i in range(len(cases))]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errors, errors
+    for i, (outs, grad) in enumerate(alone):
+        for a, b in zip(outs, results[i][0]):
+            assert torch.equal(a, b), f"thread {i}: lookup differs from the single-threaded run"
+        assert torch.equal(grad, results[i][1]), f"thread {i}: gradient differs from the single-threaded run"
+    # an error raised in one thread leaves the other threads' error state alone
+    with pytest.raises(RuntimeError):
+        sb.CorrBlock1D(cases[0][0], cases[1][1])        # mismatched shapes
