@@ -28,8 +28,9 @@ def launch_summary():
         t[1] += 1
     s = sum(t[0] for t in tot.values())
     with open(os.path.join(DST, "launches_bench_summary.txt"), "w") as f:
-        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none of `python bench.py --steps 2 --warmup 3 "
-                "--no-cpu-baseline --configs cfg2,cfg3` (cold-cache, serialised replays: shares, not absolutes)\n")
+        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 of `python bench.py --steps 2 --warmup 3 "
+                "--reps 1 --no-cpu-baseline --configs none` (tools/collect_launch_list.sh; first 3000 launches; "
+                "cold-cache, serialised replays: shares, not absolutes)\n")
         for k, (v, n) in sorted(tot.items(), key=lambda kv: -kv[1][0]):
             f.write(f"{v:10.1f} us {100*v/s:5.1f}%  n={n:4d} avg={v/n:8.2f} us  {k[:110]}\n")
     # the full per-launch list is 700 KB: keep the first 400 launches (warm-up + timed cfg1 steps) verbatim
