@@ -708,6 +708,9 @@ def main():
     bflags = graphs[0][1][0]._state.build_flags      # what CorrBlock1D passes (levels 1/3 not written)
     bd_graph = capture(torch, side, lambda: [_build_into(pyrs[s], sets[s][0], sets[s][1], bflags) for s in range(nsets)])
     t_lookup_alone = timer(lambda i: lk_graphs[i % nsets][0].replay(), 50, warm=5) / iters
+    # the same graph replayed on ONE input set: pyramid and coordinates L2-resident, i.e. where a real
+    # update loop leaves them (the GRU has just written coords1); reported next to the cold-input numbers
+    t_lookup_warm = timer(lambda i: lk_graphs[0][0].replay(), 50, warm=5) / iters
     t_build = timer(lambda i: bd_graph[0].replay(), 50, warm=5) / nsets
     # the lookup's duration INSIDE the timed step (pyramid just written by the build, L2-warm):
     # (step - build) / iters, from the same CUDA-event timing as `value`
@@ -739,8 +742,12 @@ def main():
                                               "is L2-resident and only the coordinates and outputs touch DRAM")
     roofline["kernel"] = kname
     roofline["us_per_launch_standalone"] = t_lookup_alone * 1e6
+    roofline["us_per_launch_l2_warm_inputs"] = t_lookup_warm * 1e6
+    roofline["frac_l2_warm_inputs"] = lookup_bytes / t_lookup_warm / 1e9 / hbm_peak
     roofline["how"] = ("(event-timed step - event-timed build) / 32 lookups, i.e. the launches inside the timed "
-                       "region; us_per_launch_standalone = lookups-only graphs over rotating (L2-cold) input sets")
+                       "region; us_per_launch_standalone = lookups-only graphs over rotating (L2-cold) input sets; "
+                       "us_per_launch_l2_warm_inputs = the same graph replayed on one set (pyramid AND coordinates in L2, "
+                       "as after a GRU update), not the timed region")
     roofline["traffic_note"] = ("ncu cold-cache replay (profiles/r02); inside the timed step the pyramid is "
                                 "L2-resident and DRAM traffic is ~0" if not big else "ncu capture, profiles/r02")
     roofline["note"] = ("pyramid of this workload (%.0f MB) fits the 126 MB L2: bandwidth is L2-assisted and the "
@@ -958,6 +965,7 @@ def main():
             "eager_api_pairs_per_s_output_ring": B / t_eager_ring,
             "breakdown_us": {"build": t_build * 1e6, "lookup_per_iter_in_step": t_lookup * 1e6,
                              "lookup_per_iter_standalone": t_lookup_alone * 1e6,
+                             "lookup_per_iter_l2_warm_inputs": t_lookup_warm * 1e6,
                              "graph_step": 1e6 * dev_s / args.steps},
             "configs": configs,
             "strong_scaling": strong or None,
