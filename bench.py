@@ -507,6 +507,37 @@ def measure_config(ctx, name, B=None, H=None, reps=20):
     return res
 
 
+def measure_fp16(ctx, name, reps=20):
+    """The reference's "reg_cuda" mode under its default mixed precision (core/SMoEStereo.py:217-218,
+    core/corr.py:31-61): fp16 feature maps -> fp16 pyramid (tcgen05 kind::f16) -> fp16 lookups, what
+    CorrBlockFast1D runs.  Whole config on this rank (N=1 only); same graphs as measure_config."""
+    torch, sb, dev, side, timer = ctx["torch"], ctx["sb"], ctx["dev"], ctx["side"], ctx["timer"]
+    from smoe_stereo_b200.corr import _build_into, _lookup
+    wl = WORKLOADS[name]
+    B, C, H, W, L, r, iters = (wl[k] for k in ("B", "C", "H", "W", "L", "r", "iters"))
+    px = B * H * W
+    f1, f2, coords = synth_inputs_gpu(torch, wl, B, H, seed=7100 + ctx["rank"], dev=dev)
+    f1, f2 = f1.half(), f2.half()
+    pyr = sb.FusedPyramid(B, H, W, W, L, torch.float16, dev)
+    flags = sb._lib.BUILD_SKIP_ODD_LEVELS
+    widths = pyr.widths
+    g_build = capture(torch, side, lambda: _build_into(pyr, f1, f2, flags))
+    g_look = capture(torch, side, lambda: [_lookup(pyr, coords[t], r, torch.float16) for t in range(iters)])
+    t_build = timer(lambda i: g_build[0].replay(), reps)
+    t_look = timer(lambda i: g_look[0].replay(), reps) / iters
+    hbm, src = ctx["hbm_peak"], ctx["peak_src"]
+    moved = 2 * B * C * H * W * 2 + px * sum(w for i, w in enumerate(widths) if i % 2 == 0) * 2
+    look_bytes = px * (4 + L * (2 * r + 2) * 2 + L * (2 * r + 1) * 2)
+    res = {"workload": wl["desc"] + " -- fp16 feature maps, fp16 pyramid, fp16 lookup outputs (CorrBlockFast1D / reg_cuda)",
+           "pyramid_mb": pyr.buffer.numel() * 2 / 1e6,
+           "roofline_build": roof(moved, t_build, hbm, src), "roofline_lookup": roof(look_bytes, t_look, hbm, src),
+           "ms_per_step_sum": (t_build + iters * t_look) * 1e3,
+           "breakdown_us": {"build": t_build * 1e6, "lookup_per_iter": t_look * 1e6}}
+    res["roofline_build"]["kernel"] = "corr_build_kernel<__half,__half,false,false>"
+    res["roofline_lookup"]["kernel"] = "lookup_fwd_px_kernel<__half,__half,4,4,...>"
+    return res
+
+
 def measure_cfg5(ctx, frames=3):
     """BASELINE config 5: the UNMODIFIED reference SMoEStereo (DAMv2 ViT-L + SMoE PEFT, random init,
     baseline/_ref) on a 540x960 frame padded to 544x960, 32 iterations, default mixed precision --
@@ -913,6 +944,12 @@ def main():
             del sample
         except Exception as e:      # noqa: BLE001  (a failing extra config must not take the headline down)
             configs[name] = {"error": f"{type(e).__name__}: {e}"}
+        torch.cuda.empty_cache()
+    if world == 1 and "cfg3" in extra:
+        try:
+            configs["cfg3_reg_cuda_fp16"] = measure_fp16(ctx, "cfg3")
+        except Exception as e:      # noqa: BLE001
+            configs["cfg3_reg_cuda_fp16"] = {"error": f"{type(e).__name__}: {e}"}
         torch.cuda.empty_cache()
     roofline_hbm = None
     if "cfg3" in configs and "roofline_lookup" in configs["cfg3"]:
