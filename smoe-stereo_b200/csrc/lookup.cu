@@ -84,6 +84,9 @@ __device__ __forceinline__ void st_hint(__half* p, __half v, unsigned long long 
 // SM holds.  In steady state (32 lookups back to back) the kernel moves 59.6 MB of DRAM reads (64-byte
 // fills around 80-byte segments; 39 MB useful) + 34.5 MB of output per config-3 launch in 17.9 us =
 // 5.3 TB/s, 80 % of the measured copy peak: it is DRAM-bound on the bytes the fill granularity forces.
+// Also rejected (profiles/r02/lookup_thread_per_level_variant.log): one thread per output LEVEL for
+// L2-resident volumes (both threads of a level pair gather the segment, one interpolates the fine level,
+// the other recomputes the coarse one): the cfg1 step went from 134-138 to 157 us.
 template <typename VT, typename OT, int R, int NL, bool STREAM, bool SPLIT, bool LD256 = false, int HINT = 0>
 __global__ void __launch_bounds__(256)
 lookup_fwd_px_kernel(PyrDev pyr, const float* __restrict__ coords, long long coords_bstride,
