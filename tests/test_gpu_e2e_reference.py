@@ -59,6 +59,16 @@ def _stock_vs_installed(model, impl, left, right, iters=32, stock_impl=None):
     stock = _disp(model, left, right, iters)
     stock2 = _disp(model, left, right, iters)                  # run-to-run noise floor of the stock arm
     replaced = sb.install()
+    import smoe_stereo_b200.corr as our_corr
+    calls = {"n": 0, "dtypes": set()}
+    real_lookup = our_corr._lookup
+
+    def counting_lookup(pyr, coords, radius, out_dtype, *a, **k):
+        calls["n"] += 1
+        calls["dtypes"].add((pyr.dtype, out_dtype))
+        return real_lookup(pyr, coords, radius, out_dtype, *a, **k)
+
+    our_corr._lookup = counting_lookup
     try:
         assert any(r.endswith(".CorrBlock1D") for r in replaced), replaced
         import core.raft_stereo as rs
@@ -66,11 +76,13 @@ def _stock_vs_installed(model, impl, left, right, iters=32, stock_impl=None):
         model.args.corr_implementation = impl
         ours = _disp(model, left, right, iters)
     finally:
+        our_corr._lookup = real_lookup
         sb.uninstall()
     assert _loaded_native_lib(), "libsmoecorr.so was not loaded: the drop-in did not run the CUDA path"
+    assert calls["n"] >= iters, f"the installed arm made {calls['n']} lookups through this package, expected >= {iters}"
     d = (stock - ours).abs()
     return dict(epe=d.mean().item(), epe_max=d.max().item(), floor=(stock - stock2).abs().mean().item(),
-                disp=stock.abs().mean().item())
+                disp=stock.abs().mean().item(), lookups=calls["n"], dtypes=calls["dtypes"])
 
 
 @pytest.fixture(scope="module")
@@ -189,3 +201,24 @@ def test_channels_last_producer_feeds_the_build_in_place(raft_fp32):
     epe = (stock - ours).abs().mean().item()
     print(f"\n[e2e RAFTStereo channels-last producer] EPE vs stock NCHW {epe:.3e} px")
     assert epe <= EPE_TOL
+
+
+def test_raftstereo_reg_cuda_under_autocast_fp16_path(raft_fp32):
+    """The mode that actually runs under the reference's defaults when reg_cuda is selected:
+    mixed_precision=True keeps the feature maps in fp16 (core/raft_stereo.py:183-184), so the volume, the
+    pyramid and every lookup are fp16 -- stock arm = the reference's own CUDA sampler (oracle/_ref),
+    ours = tcgen05 kind::f16 build + fp16 lookup kernels.  fp16 GRU arithmetic amplifies 1-ulp
+    differences of the volume; bound = max(north_star, 3x the stock arm's run-to-run floor)."""
+    if not R.ref_sampler_available():
+        pytest.skip("oracle/_ref/corr_sampler_ref.so not built (oracle/build_ref_sampler.py)")
+    model, left, right = raft_fp32
+    model.args.mixed_precision = True
+    try:
+        r = _stock_vs_installed(model, "reg_cuda", left, right, 32)
+    finally:
+        model.args.mixed_precision = False
+    print(f"\n[e2e RAFTStereo reg_cuda, autocast: fp16 volume + fp16 lookups] mean|disp| {r['disp']:.3f} px  "
+          f"EPE {r['epe']:.3e} px (max {r['epe_max']:.3e}; stock run-to-run {r['floor']:.1e})")
+    assert r["disp"] > 0.05
+    assert r["dtypes"] == {(torch.float16, torch.float16)}, r["dtypes"]      # fp16 pyramid, fp16 lookups
+    assert r["epe"] <= max(EPE_TOL, 3 * r["floor"])

@@ -15,12 +15,17 @@ from smoe_stereo_b200.corr import (_batchable, _batched_lookup_backward, _build_
                                    _lookup)
 
 cfg, what = sys.argv[1], sys.argv[2]
-n = int(sys.argv[3]) if len(sys.argv) > 3 else 4
+half = "--fp16" in sys.argv            # reg_cuda: fp16 feature maps, fp16 pyramid, fp16 lookups
+argv = [a for a in sys.argv if a != "--fp16"]
+n = int(argv[3]) if len(argv) > 3 else 4
 wl = WORKLOADS[cfg]
 dev = torch.device("cuda", 0)
 B, C, H, W, L, r, iters = (wl[k] for k in ("B", "C", "H", "W", "L", "r", "iters"))
 f1, f2, coords = synth_inputs_gpu(torch, wl, B, H, seed=7000, dev=dev)
-pyr = sb.FusedPyramid(B, H, W, W, L, torch.float32, dev)
+vdt = torch.float16 if half else torch.float32
+if half:
+    f1, f2 = f1.half(), f2.half()
+pyr = sb.FusedPyramid(B, H, W, W, L, vdt, dev)
 flags = sb._lib.BUILD_SKIP_ODD_LEVELS
 _build_into(pyr, f1, f2, flags)
 torch.cuda.synchronize()
@@ -33,7 +38,7 @@ if what == "build":
 elif what == "lookup":
     a.record()
     for t in range(n):
-        keep.append(_lookup(pyr, coords[t % iters], r, torch.float32))
+        keep.append(_lookup(pyr, coords[t % iters], r, vdt))
 elif what in ("lookup_bwd", "build_bwd"):
     g = torch.Generator(device=dev).manual_seed(9000)
     gouts = [torch.randn((B, L * (2 * r + 1), H, W), device=dev, generator=g) for _ in range(iters)]
