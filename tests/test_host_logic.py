@@ -106,3 +106,22 @@ def test_install_rebinds_every_reference_binding():
     finally:
         sb.uninstall()
     assert c.CorrBlock1D is stock and rs.CorrBlock1D is stock
+
+
+def test_install_output_ring_sets_and_clears_the_default():
+    """install(output_ring=n) is the opt-in switch for the lookup output ring; uninstall() clears it."""
+    import smoe_stereo_b200 as sb
+    import smoe_stereo_b200.corr as c
+    assert c._default_output_ring == 0
+    try:
+        sb.install(output_ring=3)
+        assert c._default_output_ring == 3
+        sb.install()                         # a plain install() resets the option
+        assert c._default_output_ring == 0
+        sb.set_default_output_ring(-5)       # negative depths mean "off"
+        assert c._default_output_ring == 0
+        sb.set_default_output_ring(2)
+        assert c._default_output_ring == 2
+    finally:
+        sb.uninstall()
+    assert c._default_output_ring == 0
