@@ -153,7 +153,8 @@ def test_native_build_backward_vs_oracle(sb, oracle, shape):
     assert e1 < E2E_GRAD_TOL and e2 < E2E_GRAD_TOL
 
 
-@pytest.mark.parametrize("shape,T,gdtype", [((2, 80, 184), 5, torch.float32), ((1, 135, 240), 3, torch.float32),
+@pytest.mark.parametrize("shape,T,gdtype", [((8, 80, 184), 22, torch.float32),     # BASELINE config 2, full size
+                                            ((2, 80, 184), 5, torch.float32), ((1, 135, 240), 3, torch.float32),
                                             ((1, 6, 52), 50, torch.float32), ((2, 8, 40), 4, torch.float16),
                                             ((2, 5, 37), 3, torch.float32),     # H*W1 % 4 != 0, odd widths
                                             ((1, 3, 21), 2, torch.float16)])    # ragged 32-pixel tiles, fp16 grads
