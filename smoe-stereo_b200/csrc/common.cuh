@@ -291,4 +291,36 @@ template <int N> struct LerpChunk<__half, N> {
   }
 };
 
+// The N taps of a window: out[k] = lerp(v[k], v[k+1]), k < N, in LT's arithmetic.  Generic: lerp_ref
+// per tap.  LT == __half: the packed native form of LerpChunk above (bit-identical to the c10::Half
+// emulation) -- what the thread-per-pixel lookup spends on its 18 taps drops from ~9 to ~3
+// instructions per tap.
+template <typename LT, int N> struct LerpTaps {
+  __device__ static __forceinline__ void run(const float* v, float dx, float (&out)[N]) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) out[k] = to_float(lerp_ref<LT>(v[k], v[k + 1], dx));
+  }
+};
+template <int N> struct LerpTaps<__half, N> {
+  __device__ static __forceinline__ void run(const float* v, float dx, float (&out)[N]) {
+    constexpr int P = (N + 2) / 2;                                     // half2 registers covering v[0..N]
+    const __half2 w1 = __float2half2_rn(1.0f - dx);
+    const __half2 w0 = __float2half2_rn(dx);
+    __half2 a[P], b[P];
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+      const __half2 h = __floats2half2_rn(v[2 * i], (2 * i + 1 <= N) ? v[2 * i + 1] : 0.f);   // exact: fp16 values
+      a[i] = __hmul2_rn(h, w1);
+      b[i] = __hmul2_rn(h, w0);
+    }
+#pragma unroll
+    for (int i = 0; 2 * i < N; ++i) {
+      const __half2 bs = __halves2half2(__high2half(b[i]), (i + 1 < P) ? __low2half(b[i + 1]) : __float2half_rn(0.f));
+      const float2 f = __half22float2(__hadd2_rn(a[i], bs));
+      out[2 * i] = f.x;
+      if (2 * i + 1 < N) out[2 * i + 1] = f.y;
+    }
+  }
+};
+
 }  // namespace smoe

@@ -90,16 +90,14 @@ struct PxPair {
         if (cs * (EPL / 2) + j >= wc) pc[j] = 0.f;
     }
     shift_down<NV / 2, LOG_EPL - 1>(pc, sh >> 1);
-#pragma unroll
-    for (int k = 0; k < RD; ++k) out[k] = to_float(lerp_ref<LT>(pc[k], pc[k + 1], dxc));
+    LerpTaps<LT, RD>::run(pc, dxc, out);
   }
 
   // Interpolated taps of the fine level: the window starts R + odd elements after the segment start.
   template <typename LT>
   __device__ __forceinline__ void fine(float (&out)[RD]) {
     shift_down<NV, LOG_EPL>(v, sh + (odd > 0 ? 1 : 0));
-#pragma unroll
-    for (int k = 0; k < RD; ++k) out[k] = to_float(lerp_ref<LT>(v[R + k], v[R + k + 1], dxf));
+    LerpTaps<LT, RD>::run(v + R, dxf, out);
   }
 };
 
@@ -187,15 +185,13 @@ struct PxPair256 {
         if ((unsigned)(c0 + j) >= (unsigned)wc) pc[j] = 0.f;
     }
     shift_down<NV / 2, 2>(pc, sh >> 1);
-#pragma unroll
-    for (int k = 0; k < RD; ++k) out[k] = to_float(lerp_ref<LT>(pc[k], pc[k + 1], dxc));
+    LerpTaps<LT, RD>::run(pc, dxc, out);
   }
 
   template <typename LT>
   __device__ __forceinline__ void fine(float (&out)[RD]) {
     shift_down<NV, 3>(v, sh + (odd > 0 ? 1 : 0));
-#pragma unroll
-    for (int k = 0; k < RD; ++k) out[k] = to_float(lerp_ref<LT>(v[R + k], v[R + k + 1], dxf));
+    LerpTaps<LT, RD>::run(v + R, dxf, out);
   }
 };
 
