@@ -10,7 +10,7 @@ step    : one pass of the hot path over one stereo pair: volume+pyramid build (1
           + 32 fused pyramid lookups (32 kernels), i.e. 33 launches of our own kernels.
 value   : pairs/s with inputs resident in HBM, the step replayed as a CUDA graph, timed with CUDA
           events on the launching stream; steps rotate over several independent input sets whose
-          combined footprint exceeds the 126 MB L2 (stated in config.l2).  value_stats repeats the
+          combined footprint exceeds the 126 MB L2 (stated in config.l2 / run.l2).  value_stats repeats the
           timed region so that one line is self-validating.
 e2e     : pairs/s through the public API (CorrBlock1D(...) + __call__) with HOST buffers: pinned
           host feature maps / coords copied H2D and every lookup result copied D2H inside the
@@ -245,6 +245,14 @@ class PytorchReferencePath:
         return times, ctor
 
 
+def bench_config(wl):
+    """`config` of the JSON line -- the SAME dict in the GPU arm and in the reference arm (the driver compares
+    them); what is specific to an arm (input-set count, launch mode, CPU model) goes to `run`."""
+    return {"workload": wl["desc"],
+            "l2": "GPU arm: steps rotate over independent input sets whose combined footprint exceeds the 126 MB L2 "
+                  "(count and bytes in run.l2); CPU arm: one input set in host memory"}
+
+
 def cpu_model():
     try:
         for line in open("/proc/cpuinfo"):
@@ -295,7 +303,8 @@ def run_reference_arm(args, wl, rank, world):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": wl["desc"], "device": "host CPU", "cpu": cpu_model()},
+        "data": "synthetic", "config": bench_config(wl),
+        "run": {"device": "host CPU", "cpu": cpu_model()},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
                          "constructor_ms": ctor_ms},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -995,9 +1004,11 @@ def main():
             "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "tf32 (fp32 in/out, fp32 accumulate)",
             "data": "synthetic",
-            "config": {"workload": wl["desc"], "per_gpu_batch": B, "partitioning": f"batch x{world}, no collective",
-                       "l2": f"steps rotate over {nsets} independent input sets ({nsets * set_bytes / 1e6:.0f} MB > 126 MB L2)",
-                       "launch": "one CUDA graph per step (1 build + 32 lookup kernels)"},
+            # `config` is identical in both arms (the driver compares them); how this arm runs it is in `run`
+            "config": bench_config(wl),
+            "run": {"per_gpu_batch": B, "partitioning": f"batch x{world}, no collective",
+                    "l2": f"steps rotate over {nsets} independent input sets ({nsets * set_bytes / 1e6:.0f} MB > 126 MB L2)",
+                    "launch": "one CUDA graph per step (1 build + 32 lookup kernels)"},
             "value_stats": value_stats,
             "e2e": e2e, "gpu_launches": args.steps * (1 + iters),
             "roofline": roofline, "roofline_build": roofline_build, "roofline_hbm": roofline_hbm,
