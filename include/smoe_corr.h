@@ -13,6 +13,7 @@
  *   smoe_corr_build            core/corr.py:148-156 (CorrBlock1D.corr: einsum + /sqrt(D))
  *                              + core/corr.py:119-125 / :38-42 (avg_pool2d pyramid)
  *   smoe_corr_lookup           core/corr.py:127-146 (CorrBlock1D.__call__), core/corr.py:44-51
+ *   smoe_corr_lookup_to        the same + the output gather of nn.DataParallel, train_stereo_sceneflow.py:133
  *                              (CorrBlockFast1D.__call__), sampler/sampler.cpp:24-32 and
  *                              sampler/sampler_kernel.cu:19-60,107-136 (corr_sampler.forward)
  *   smoe_corr_lookup_update    the loop glue of core/SMoEStereo.py:234-248 + the lookup (opt-in)
@@ -167,6 +168,26 @@ int smoe_corr_lookup(const smoe_pyramid_t* pyr, const float* coords, int64_t coo
 int smoe_corr_lookup_update(const smoe_pyramid_t* pyr, const float* coords1, const float* delta_flow,
                             const float* coords0, float* coords1_out, float* flow_out, int radius,
                             void* out, int out_dtype, smoe_stream_t stream);
+
+/*
+ * Lookup written through a caller-described view of a larger output, optionally a multicast address:
+ * the fused form of "lookup, then all-gather the result" for a path that is sharded by batch or by
+ * image rows over the GPUs of one NVSwitch domain (the reference's counterpart is the
+ * gather nn.DataParallel performs on the outputs, train_stereo_sceneflow.py:133).
+ *   element (b, ch, y, x) of this rank's lookup goes to  out + b*out_batch_stride + ch*out_channel_stride
+ *   + y*W1 + x  (strides in elements; the caller has already offset `out` to its shard's place)
+ *   SMOE_OUT_MULTIMEM: `out` is a multicast (NVLS) address mapped over one buffer per GPU; every value
+ *   is stored once with multimem.st and the switch replicates it into all of them.  The caller owns
+ *   the cross-GPU synchronisation that makes the result visible (a barrier after the call).
+ * Covers radius 4, 3 or 4 levels, fp32 outputs, pyramids laid out by smoe_corr_pyramid_layout; other
+ * cases return SMOE_ERR_UNSUPPORTED (use smoe_corr_lookup and a collective).  Values are bit-identical
+ * to smoe_corr_lookup.
+ */
+#define SMOE_OUT_MULTIMEM 1u
+int smoe_corr_lookup_to(const smoe_pyramid_t* pyr, const float* coords, int64_t coords_batch_stride,
+                        float coord_scale, int radius, void* out, int64_t out_batch_stride,
+                        int64_t out_channel_stride, int out_dtype, unsigned out_flags,
+                        smoe_stream_t stream);
 
 /*
  * Lookup fused with the 1x1 convolution that consumes it (opt-in extension):

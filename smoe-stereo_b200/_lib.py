@@ -20,6 +20,7 @@ BUILD_TF32_TRUNCATE = 1
 BUILD_CHANNELS_LAST = 2
 BUILD_SKIP_ODD_LEVELS = 4
 BWD_OVERWRITE, BWD_ACCUMULATE = 0, 1
+OUT_MULTIMEM = 1
 MAX_BATCHED_ITERS = 48
 
 # every symbol include/smoe_corr.h declares
@@ -28,7 +29,7 @@ SYMBOLS = (
     "smoe_corr_pyramid_layout", "smoe_corr_build_workspace_bytes", "smoe_corr_build",
     "smoe_corr_lookup", "smoe_corr_lookup_bwd", "smoe_corr_fold_pyramid_grad",
     "smoe_corr_fill_levels", "smoe_corr_build_bwd", "smoe_corr_lookup_update",
-    "smoe_corr_lookup_bwd_batched", "smoe_corr_lookup_conv1x1",
+    "smoe_corr_lookup_bwd_batched", "smoe_corr_lookup_conv1x1", "smoe_corr_lookup_to",
 )
 # only in the cross-check library (tests/_build/libsmoecorr_xcheck.so, csrc/xcheck_api.h)
 XCHECK_SYMBOLS = ("smoe_corr_debug_set_timeline", "smoe_corr_debug_set_lookup_kernel",
@@ -70,6 +71,8 @@ def _declare(L: ctypes.CDLL) -> None:
     L.smoe_corr_lookup_bwd.argtypes = [pp, vp, i64, f32, i32, vp, i32, i32, vp]
     L.smoe_corr_lookup_update.argtypes = [pp, vp, vp, vp, vp, vp, i32, vp, i32, vp]
     L.smoe_corr_lookup_update.restype = i32
+    L.smoe_corr_lookup_to.argtypes = [pp, vp, i64, f32, i32, vp, i64, i64, i32, ctypes.c_uint, vp]
+    L.smoe_corr_lookup_to.restype = i32
     L.smoe_corr_lookup_conv1x1.argtypes = [pp, vp, i64, f32, i32, i32, vp, vp, i32, i32, vp, i32, vp]
     L.smoe_corr_lookup_conv1x1.restype = i32
     L.smoe_corr_lookup_bwd_batched.argtypes = [pp, i32, i32, vp, vp, vp, i32, i32, i32, vp]

@@ -1271,6 +1271,57 @@ static int launch_bwd_dense(const smoe_pyramid_t* gp, const PyrDev& d, const flo
 }  // namespace smoe
 
 namespace smoe {
+// ------------------------------------------------------- forward into a strided / multicast view
+// smoe_corr_lookup_to: the lookup of THIS rank's shard written straight into its place inside a larger
+// (gathered) output -- element (b, ch, hw) goes to out + b*obs + ch*ocs + hw -- and, with MM, through
+// an NVSwitch MULTICAST address: one multimem.st per value and the switch replicates it into the
+// corresponding buffer of every GPU of the group.  That is lookup + all-gather in one kernel (the
+// counterpart of nn.DataParallel's gather of the outputs, train_stereo_sceneflow.py:133): no NCCL
+// kernel, no second pass over the result, the transfer overlaps the gathers of the other warps.
+// Same gather (PxPair / PxPair256) and arithmetic as lookup_fwd_px_kernel => bit-identical values.
+__device__ __forceinline__ void st_multimem(float* p, float v) {
+  asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+template <typename VT, int NL, bool STREAM, bool LD256, bool MM>
+__global__ void __launch_bounds__(256)
+lookup_fwd_px_to_kernel(PyrDev pyr, const float* __restrict__ coords, long long coords_bstride,
+                        float coord_scale, float* __restrict__ out, long long obs, long long ocs, int HW) {
+  using Pair = typename std::conditional<LD256, PxPair256<STREAM>, PxPair<VT, STREAM>>::type;
+  constexpr int R = 4, RD = 2 * R + 1, NP = (NL + 1) / 2;
+  static_assert(NP == 2 && (!LD256 || sizeof(VT) == 4), "3- or 4-level pyramids; 256-bit loads for fp32 volumes");
+  pdl_wait();
+  const int b = blockIdx.y;
+  const int hw = blockIdx.x * blockDim.x + threadIdx.x;
+  const int pr = threadIdx.y;                              // one thread per level pair
+  if (hw >= HW) return;
+  const CoordUpd none = {nullptr, nullptr, nullptr, nullptr, 0};
+  const float x0 = fetch_coord(coords, coords_bstride, none, b, hw, false) * coord_scale;
+  const long long row = (long long)b * HW + hw;
+  const bool first = pr == 0;
+  const VT* fine_row = static_cast<const VT*>(first ? pyr.ptr[0] : pyr.ptr[2]) + row * (first ? pyr.pitch[0] : pyr.pitch[2]);
+  Pair pair;
+  pair.load(reinterpret_cast<const typename std::conditional<LD256, float, VT>::type*>(fine_row),
+            first ? pyr.width[0] : pyr.width[2], x0 * (first ? 1.0f : 0.25f), 0);
+  pdl_launch_dependents();
+  auto put = [&](float* p, float v) {
+    if (MM) st_multimem(p, v);
+    else *p = v;
+  };
+  float* dst = out + (long long)b * obs + hw;
+  const int lf = 2 * pr;
+  float e[RD];
+  if (lf + 1 < NL) {
+    pair.template coarse<float>(first ? pyr.width[1] : pyr.width[3], e);
+    float* d1 = dst + (long long)(lf + 1) * RD * ocs;
+#pragma unroll
+    for (int k = 0; k < RD; ++k) put(d1 + (long long)k * ocs, e[k]);
+  }
+  pair.template fine<float>(e);
+  float* d0 = dst + (long long)lf * RD * ocs;
+#pragma unroll
+  for (int k = 0; k < RD; ++k) put(d0 + (long long)k * ocs, e[k]);
+}
+
 static int lookup_impl(const smoe_pyramid_t* pyr, const float* coords, int64_t coords_batch_stride,
                        float coord_scale, int radius, void* out, int out_dtype, smoe_stream_t stream,
                        const CoordUpd& upd) {
@@ -1337,6 +1388,60 @@ int smoe_corr_lookup(const smoe_pyramid_t* pyr, const float* coords, int64_t coo
                      smoe_stream_t stream) {
   const smoe::CoordUpd none = {nullptr, nullptr, nullptr, nullptr, 0};
   return smoe::lookup_impl(pyr, coords, coords_batch_stride, coord_scale, radius, out, out_dtype, stream, none);
+}
+
+int smoe_corr_lookup_to(const smoe_pyramid_t* pyr, const float* coords, int64_t coords_batch_stride,
+                        float coord_scale, int radius, void* out, int64_t out_batch_stride,
+                        int64_t out_channel_stride, int out_dtype, unsigned out_flags, smoe_stream_t stream) {
+  using namespace smoe;
+  if (int rc = validate_pyramid(pyr, "lookup_to")) return rc;
+  const long long HW = (long long)pyr->H * pyr->W1;
+  if (pyr->B == 0 || HW == 0) return SMOE_OK;
+  SMOE_REQUIRE(coords && out, SMOE_ERR_INVALID_ARG, "lookup_to: NULL coords/out pointer");
+  SMOE_REQUIRE(coords_batch_stride >= HW, SMOE_ERR_INVALID_ARG,
+               "lookup_to: coords batch stride %lld < H*W1 %lld", (long long)coords_batch_stride, HW);
+  SMOE_REQUIRE((out_flags & ~SMOE_OUT_MULTIMEM) == 0, SMOE_ERR_INVALID_ARG, "lookup_to: unknown flags 0x%x", out_flags);
+  // the fused gather covers what a sharded CorrBlock1D produces: radius 4, 3 or 4 levels, fp32 outputs,
+  // vector-aligned pyramid; everything else -> SMOE_ERR_UNSUPPORTED (use smoe_corr_lookup + a collective)
+  SMOE_REQUIRE(radius == 4 && (pyr->num_levels == 3 || pyr->num_levels == 4) && out_dtype == SMOE_DTYPE_F32 &&
+                   pyramid_vec_ok(pyr) && (pyr->levels_missing & 0x5) == 0 && pyr->B <= 65535,
+               SMOE_ERR_UNSUPPORTED, "lookup_to: radius %d / %d levels / out dtype %d not covered", radius,
+               pyr->num_levels, out_dtype);
+  SMOE_REQUIRE(out_channel_stride >= HW && out_batch_stride >= out_channel_stride * pyr->num_levels * 9,
+               SMOE_ERR_INVALID_ARG, "lookup_to: output strides (%lld, %lld) overlap", (long long)out_batch_stride,
+               (long long)out_channel_stride);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const PyrDev d = to_dev(pyr);
+  const bool mm = (out_flags & SMOE_OUT_MULTIMEM) != 0;
+  const bool f16v = pyr->dtype == SMOE_DTYPE_F16;
+  const bool big = volume_exceeds_l2(d, HW * pyr->B, f16v ? 2 : 4);
+  const bool ld256 = !f16v && big && pyramid_ld256_ok(d, pyr->num_levels);
+  dim3 grid((unsigned)((HW + 31) / 32), pyr->B), block(32, 2);
+  float* o = static_cast<float*>(out);
+  const long long obs = out_batch_stride, ocs = out_channel_stride;
+#define SMOE_TO(VT, NLV, STR, L256)                                                                          \
+  do {                                                                                                       \
+    if (mm) launch_kernel_pdl(lookup_fwd_px_to_kernel<VT, NLV, STR, L256, true>, grid, block, 0, st, d, coords, \
+                              (long long)coords_batch_stride, coord_scale, o, obs, ocs, (int)HW);            \
+    else launch_kernel_pdl(lookup_fwd_px_to_kernel<VT, NLV, STR, L256, false>, grid, block, 0, st, d, coords, \
+                           (long long)coords_batch_stride, coord_scale, o, obs, ocs, (int)HW);               \
+  } while (0)
+#define SMOE_TO_NL(VT, STR, L256)                                                                            \
+  do {                                                                                                       \
+    if (pyr->num_levels == 4) SMOE_TO(VT, 4, STR, L256); else SMOE_TO(VT, 3, STR, L256);                     \
+  } while (0)
+  if (f16v) {
+    if (big) SMOE_TO_NL(__half, true, false); else SMOE_TO_NL(__half, false, false);
+  } else if (ld256) {
+    SMOE_TO_NL(float, true, true);
+  } else if (big) {
+    SMOE_TO_NL(float, true, false);
+  } else {
+    SMOE_TO_NL(float, false, false);
+  }
+#undef SMOE_TO_NL
+#undef SMOE_TO
+  return check_launch("lookup forward (strided / multicast output)");
 }
 
 int smoe_corr_lookup_update(const smoe_pyramid_t* pyr, const float* coords1, const float* delta_flow,

@@ -59,6 +59,47 @@ def gather_lookup(local: torch.Tensor, mode: str, full_extent: int, group=None) 
     return torch.cat(parts, dim=0).movedim(0, d).contiguous()
 
 
+class FusedGather:
+    """Lookup + all-gather in ONE kernel (smoe_corr_lookup_to): every rank's lookup kernel stores its
+    shard of the result through an NVSwitch MULTICAST address (`multimem.st`), and the switch replicates
+    each value into the gathered buffer of every GPU of the group -- no NCCL kernel, no second pass
+    over the result.  The buffers are torch symmetric-memory allocations (one (B,36,H,W) fp32 tensor
+    per GPU, a ring of `depth` of them); a symmetric-memory barrier after the lookup makes the peers'
+    stores visible.  Raises if the group has no multicast mapping; use gather=True (NCCL) there."""
+
+    def __init__(self, B, C, H, W, device, group=None, depth=2):
+        import torch.distributed._symmetric_memory as symm
+        self.shape = (B, C, H, W)
+        self.depth = depth
+        self.buf = symm.empty((depth, B, C, H, W), dtype=torch.float32, device=device)
+        self.hdl = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        self.mc_ptr = int(self.hdl.multicast_ptr or 0)
+        if not self.mc_ptr:
+            raise RuntimeError("the process group's GPUs have no multicast (NVLS) mapping for symmetric memory")
+        self.pos = 0
+
+    def lookup(self, block, coords, mode, lo):
+        """Run `block`'s lookup for this rank's shard (which starts at index `lo` of the sharded axis)
+        and return the FULL (B,36,H,W) result, valid on every rank after the call."""
+        from . import _lib
+        from .corr import _coords_plane, _on_device, _stream_ptr
+        B, C, H, W = self.shape
+        p = block._state.pyr
+        coords, bstride = _coords_plane(coords, p.B, p.H, p.W1)
+        slot = self.pos
+        self.pos = (self.pos + 1) % self.depth
+        plane = H * W
+        off = slot * B * C * plane + (lo * C * plane if mode == "batch" else lo * W)
+        # (a slot is reused after `depth` further lookups: the barrier of the previous use has long passed)
+        with _on_device(p.device):
+            rc = _lib.lib().smoe_corr_lookup_to(p.ref, coords.data_ptr(), bstride, 1.0, block.radius,
+                                                self.mc_ptr + 4 * off, C * plane, plane, _lib.DTYPE_F32,
+                                                _lib.OUT_MULTIMEM, _stream_ptr(p.device))
+        _lib.check(rc, "smoe_corr_lookup_to")
+        self.hdl.barrier(channel=0)
+        return self.buf[slot]
+
+
 class ShardedCorrBlock1D:
     """CorrBlock1D over this rank's batch- or row-shard of the feature maps.
 
@@ -88,10 +129,23 @@ class ShardedCorrBlock1D:
         self.block = block_cls(fmap1.contiguous(), fmap2.contiguous(), num_levels=num_levels,
                                radius=radius)
         self.num_levels, self.radius = num_levels, radius
+        self._fused = None
 
     def __call__(self, coords, gather=False):
+        """gather=False: this rank's shard of the lookup.  gather=True: the full lookup on every rank via
+        lookup + NCCL all-gather.  gather="fused": the full lookup on every rank from ONE kernel whose
+        stores go through an NVSwitch multicast address (FusedGather; fp32 "reg" blocks, radius 4, no
+        autograd); the returned tensor is a ring slot, valid until two further fused lookups."""
         if not self.already_sharded:
             coords = take_shard(coords, self.mode, self.world, self.rank).contiguous()
+        if gather == "fused" and self.world > 1:
+            if self._fused is None:
+                p = self.block._state.pyr
+                B = self.full_extent if self.mode == "batch" else p.B
+                H = self.full_extent if self.mode == "rows" else p.H
+                self._fused = FusedGather(B, p.num_levels * (2 * self.radius + 1), H, p.W1, p.device, self.group)
+            lo = shard_bounds(self.full_extent, self.world, self.rank)[0]
+            return self._fused.lookup(self.block, coords, self.mode, lo)
         out = self.block(coords)
         if gather and self.world > 1:
             out = gather_lookup(out, self.mode, self.full_extent, self.group)
