@@ -184,6 +184,7 @@ int smoe_corr_lookup_update(const smoe_pyramid_t* pyr, const float* coords1, con
  * to smoe_corr_lookup.
  */
 #define SMOE_OUT_MULTIMEM 1u
+#define SMOE_OUT_SCALAR 2u     /* debugging / A-B: 4-byte stores even where 16-byte stores are possible */
 int smoe_corr_lookup_to(const smoe_pyramid_t* pyr, const float* coords, int64_t coords_batch_stride,
                         float coord_scale, int radius, void* out, int64_t out_batch_stride,
                         int64_t out_channel_stride, int out_dtype, unsigned out_flags,

@@ -20,7 +20,7 @@ BUILD_TF32_TRUNCATE = 1
 BUILD_CHANNELS_LAST = 2
 BUILD_SKIP_ODD_LEVELS = 4
 BWD_OVERWRITE, BWD_ACCUMULATE = 0, 1
-OUT_MULTIMEM = 1
+OUT_MULTIMEM, OUT_SCALAR = 1, 2
 MAX_BATCHED_ITERS = 48
 
 # every symbol include/smoe_corr.h declares

@@ -1282,44 +1282,89 @@ namespace smoe {
 __device__ __forceinline__ void st_multimem(float* p, float v) {
   asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
-template <typename VT, int NL, bool STREAM, bool LD256, bool MM>
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ void st_multimem4(float* p, float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w) : "memory");
+}
+// VEC: the 18 channels a thread produced are transposed through a 2.3 KB shared-memory tile per warp so
+// that a lane stores 16 bytes (four consecutive pixels of one channel) -- 4.5 store instructions per
+// thread instead of 18, each a 16-byte NVLink payload per lane instead of 4 (needs H*W1 % 4 == 0 and
+// 16-byte aligned strides).
+template <typename VT, int NL, bool STREAM, bool LD256, bool MM, bool VEC>
+__global__ void __launch_bounds__(64)
 lookup_fwd_px_to_kernel(PyrDev pyr, const float* __restrict__ coords, long long coords_bstride,
                         float coord_scale, float* __restrict__ out, long long obs, long long ocs, int HW) {
   using Pair = typename std::conditional<LD256, PxPair256<STREAM>, PxPair<VT, STREAM>>::type;
   constexpr int R = 4, RD = 2 * R + 1, NP = (NL + 1) / 2;
   static_assert(NP == 2 && (!LD256 || sizeof(VT) == 4), "3- or 4-level pyramids; 256-bit loads for fp32 volumes");
+  __shared__ __align__(16) float s_tile[VEC ? 2 : 1][VEC ? 2 * RD : 1][VEC ? 32 : 1];
   pdl_wait();
   const int b = blockIdx.y;
-  const int hw = blockIdx.x * blockDim.x + threadIdx.x;
-  const int pr = threadIdx.y;                              // one thread per level pair
-  if (hw >= HW) return;
-  const CoordUpd none = {nullptr, nullptr, nullptr, nullptr, 0};
-  const float x0 = fetch_coord(coords, coords_bstride, none, b, hw, false) * coord_scale;
-  const long long row = (long long)b * HW + hw;
-  const bool first = pr == 0;
-  const VT* fine_row = static_cast<const VT*>(first ? pyr.ptr[0] : pyr.ptr[2]) + row * (first ? pyr.pitch[0] : pyr.pitch[2]);
-  Pair pair;
-  pair.load(reinterpret_cast<const typename std::conditional<LD256, float, VT>::type*>(fine_row),
-            first ? pyr.width[0] : pyr.width[2], x0 * (first ? 1.0f : 0.25f), 0);
-  pdl_launch_dependents();
-  auto put = [&](float* p, float v) {
-    if (MM) st_multimem(p, v);
-    else *p = v;
-  };
-  float* dst = out + (long long)b * obs + hw;
-  const int lf = 2 * pr;
-  float e[RD];
-  if (lf + 1 < NL) {
-    pair.template coarse<float>(first ? pyr.width[1] : pyr.width[3], e);
-    float* d1 = dst + (long long)(lf + 1) * RD * ocs;
-#pragma unroll
-    for (int k = 0; k < RD; ++k) put(d1 + (long long)k * ocs, e[k]);
+  const int lane = threadIdx.x;
+  const int hw0 = blockIdx.x * 32;
+  const int hw = hw0 + lane;
+  const int pr = threadIdx.y;                              // one thread (warp) per level pair
+  const bool live = hw < HW;
+  if constexpr (!VEC) {
+    if (!live) return;
   }
-  pair.template fine<float>(e);
-  float* d0 = dst + (long long)lf * RD * ocs;
+  const CoordUpd none = {nullptr, nullptr, nullptr, nullptr, 0};
+  const bool first = pr == 0;
+  const int lf = 2 * pr;
+  const bool has_coarse = lf + 1 < NL;
+  float ec[RD], ef[RD];
 #pragma unroll
-  for (int k = 0; k < RD; ++k) put(d0 + (long long)k * ocs, e[k]);
+  for (int k = 0; k < RD; ++k) ec[k] = ef[k] = 0.f;
+  if (live) {
+    const float x0 = fetch_coord(coords, coords_bstride, none, b, hw, false) * coord_scale;
+    const long long row = (long long)b * HW + hw;
+    const VT* fine_row = static_cast<const VT*>(first ? pyr.ptr[0] : pyr.ptr[2]) + row * (first ? pyr.pitch[0] : pyr.pitch[2]);
+    Pair pair;
+    pair.load(reinterpret_cast<const typename std::conditional<LD256, float, VT>::type*>(fine_row),
+              first ? pyr.width[0] : pyr.width[2], x0 * (first ? 1.0f : 0.25f), 0);
+    if (has_coarse) pair.template coarse<float>(first ? pyr.width[1] : pyr.width[3], ec);
+    pair.template fine<float>(ef);
+  }
+  pdl_launch_dependents();
+  float* dst = out + (long long)b * obs;
+  if constexpr (!VEC) {
+    auto put = [&](float* p, float v) {
+      if (MM) st_multimem(p, v);
+      else *p = v;
+    };
+    if (has_coarse) {
+      float* d1 = dst + (long long)(lf + 1) * RD * ocs + hw;
+#pragma unroll
+      for (int k = 0; k < RD; ++k) put(d1 + (long long)k * ocs, ec[k]);
+    }
+    float* d0 = dst + (long long)lf * RD * ocs + hw;
+#pragma unroll
+    for (int k = 0; k < RD; ++k) put(d0 + (long long)k * ocs, ef[k]);
+  } else {
+    // tile rows: [0, RD) = level lf (fine), [RD, 2*RD) = level lf + 1 (coarse): consecutive output channels
+    float (*t)[32] = s_tile[pr];
+#pragma unroll
+    for (int k = 0; k < RD; ++k) {
+      t[k][lane] = ef[k];
+      t[RD + k][lane] = ec[k];
+    }
+    __syncwarp();
+    const int nch = has_coarse ? 2 * RD : RD;
+    const int q = lane & 7, cr = lane >> 3;               // pixel quad, channel within a group of 4
+    const int px = hw0 + 4 * q;
+    if (px < HW) {                                        // (HW % 4 == 0: a quad is entirely inside or outside)
+#pragma unroll
+      for (int c0 = 0; c0 < 2 * RD; c0 += 4) {
+        const int c = c0 + cr;
+        if (c < nch) {
+          const float4 v = *reinterpret_cast<const float4*>(&t[c][4 * q]);
+          float* p = dst + (long long)(lf * RD + c) * ocs + px;
+          if (MM) st_multimem4(p, v);
+          else *reinterpret_cast<float4*>(p) = v;
+        }
+      }
+    }
+  }
 }
 
 static int lookup_impl(const smoe_pyramid_t* pyr, const float* coords, int64_t coords_batch_stride,
@@ -1400,7 +1445,8 @@ int smoe_corr_lookup_to(const smoe_pyramid_t* pyr, const float* coords, int64_t 
   SMOE_REQUIRE(coords && out, SMOE_ERR_INVALID_ARG, "lookup_to: NULL coords/out pointer");
   SMOE_REQUIRE(coords_batch_stride >= HW, SMOE_ERR_INVALID_ARG,
                "lookup_to: coords batch stride %lld < H*W1 %lld", (long long)coords_batch_stride, HW);
-  SMOE_REQUIRE((out_flags & ~SMOE_OUT_MULTIMEM) == 0, SMOE_ERR_INVALID_ARG, "lookup_to: unknown flags 0x%x", out_flags);
+  SMOE_REQUIRE((out_flags & ~(SMOE_OUT_MULTIMEM | SMOE_OUT_SCALAR)) == 0, SMOE_ERR_INVALID_ARG,
+               "lookup_to: unknown flags 0x%x", out_flags);
   // the fused gather covers what a sharded CorrBlock1D produces: radius 4, 3 or 4 levels, fp32 outputs,
   // vector-aligned pyramid; everything else -> SMOE_ERR_UNSUPPORTED (use smoe_corr_lookup + a collective)
   SMOE_REQUIRE(radius == 4 && (pyr->num_levels == 3 || pyr->num_levels == 4) && out_dtype == SMOE_DTYPE_F32 &&
@@ -1419,12 +1465,17 @@ int smoe_corr_lookup_to(const smoe_pyramid_t* pyr, const float* coords, int64_t 
   dim3 grid((unsigned)((HW + 31) / 32), pyr->B), block(32, 2);
   float* o = static_cast<float*>(out);
   const long long obs = out_batch_stride, ocs = out_channel_stride;
+  // 16-byte stores (four pixels of a channel per lane) when every address they touch is 16-byte aligned
+  const bool vec = HW % 4 == 0 && obs % 4 == 0 && ocs % 4 == 0 && aligned16(out) && (out_flags & SMOE_OUT_SCALAR) == 0;
+#define SMOE_TO_K(VT, NLV, STR, L256, MMV, VECV)                                                             \
+  launch_kernel_pdl(lookup_fwd_px_to_kernel<VT, NLV, STR, L256, MMV, VECV>, grid, block, 0, st, d, coords,   \
+                    (long long)coords_batch_stride, coord_scale, o, obs, ocs, (int)HW)
 #define SMOE_TO(VT, NLV, STR, L256)                                                                          \
   do {                                                                                                       \
-    if (mm) launch_kernel_pdl(lookup_fwd_px_to_kernel<VT, NLV, STR, L256, true>, grid, block, 0, st, d, coords, \
-                              (long long)coords_batch_stride, coord_scale, o, obs, ocs, (int)HW);            \
-    else launch_kernel_pdl(lookup_fwd_px_to_kernel<VT, NLV, STR, L256, false>, grid, block, 0, st, d, coords, \
-                           (long long)coords_batch_stride, coord_scale, o, obs, ocs, (int)HW);               \
+    if (mm && vec) SMOE_TO_K(VT, NLV, STR, L256, true, true);                                                \
+    else if (mm) SMOE_TO_K(VT, NLV, STR, L256, true, false);                                                 \
+    else if (vec) SMOE_TO_K(VT, NLV, STR, L256, false, true);                                                \
+    else SMOE_TO_K(VT, NLV, STR, L256, false, false);                                                        \
   } while (0)
 #define SMOE_TO_NL(VT, STR, L256)                                                                            \
   do {                                                                                                       \
@@ -1441,6 +1492,7 @@ int smoe_corr_lookup_to(const smoe_pyramid_t* pyr, const float* coords, int64_t 
   }
 #undef SMOE_TO_NL
 #undef SMOE_TO
+#undef SMOE_TO_K
   return check_launch("lookup forward (strided / multicast output)");
 }
 

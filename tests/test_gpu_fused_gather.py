@@ -11,9 +11,10 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+@pytest.mark.parametrize("flags", [0, 2])          # 0: 16-byte stores where alignment allows; 2 = SMOE_OUT_SCALAR
 @pytest.mark.parametrize("mode", ["batch", "rows"])
-@pytest.mark.parametrize("shape", [(2, 64, 6, 96), (3, 32, 5, 37), (1, 32, 9, 750)])
-def test_lookup_into_a_strided_view_equals_the_plain_lookup(mode, shape):
+@pytest.mark.parametrize("shape", [(2, 64, 6, 96), (3, 32, 5, 37), (1, 32, 9, 750), (2, 32, 8, 100), (1, 256, 135, 240)])
+def test_lookup_into_a_strided_view_equals_the_plain_lookup(mode, shape, flags):
     """Single GPU: every "rank's" shard is computed in turn and written straight into its place inside
     the full (B,36,H,W) tensor (batch shards: an offset; row shards: an offset and a larger channel
     stride).  The assembled tensor equals the unsharded lookup bit for bit."""
@@ -39,7 +40,7 @@ def test_lookup_into_a_strided_view_equals_the_plain_lookup(mode, shape):
         p = blk._state.pyr
         off = lo * 36 * plane if mode == "batch" else lo * W
         rc = _lib.lib().smoe_corr_lookup_to(p.ref, c.data_ptr(), c.stride(0), 1.0, 4, full.data_ptr() + 4 * off,
-                                            36 * plane, plane, _lib.DTYPE_F32, 0, _stream_ptr(dev()))
+                                            36 * plane, plane, _lib.DTYPE_F32, flags, _stream_ptr(dev()))
         _lib.check(rc, "smoe_corr_lookup_to")
     assert torch.equal(full, want)
 
