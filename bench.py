@@ -516,6 +516,51 @@ def measure_config(ctx, name, B=None, H=None, reps=20):
     return res
 
 
+def measure_fused_gather(ctx, name, world, rank):
+    """Strong-scaling configs at N > 1: the optional output gather FUSED into the lookup kernel
+    (smoe_corr_lookup_to through an NVSwitch multicast address; ShardedCorrBlock1D gather="fused")
+    next to the shard-local lookup, both as CUDA graphs of 8 lookups, max over ranks."""
+    import torch.distributed as dist
+    torch, sb, dev, side, timer = ctx["torch"], ctx["sb"], ctx["dev"], ctx["side"], ctx["timer"]
+    from smoe_stereo_b200.sharding import shard_bounds
+    full = WORKLOADS[name]
+    mode = "batch" if (full["B"] >= world and full["B"] % world == 0) else "rows"
+    ext = full["B"] if mode == "batch" else full["H"]
+    lo, hi = shard_bounds(ext, world, rank)
+    B = hi - lo if mode == "batch" else full["B"]
+    H = hi - lo if mode == "rows" else full["H"]
+    wl = dict(full)
+    f1, f2, coords = synth_inputs_gpu(torch, wl, B, H, seed=7300 + rank, dev=dev)
+    blk = sb.ShardedCorrBlock1D(f1, f2, mode=mode, already_sharded=True)
+    del f1, f2
+    c = coords[0].contiguous()
+
+    def graph_us(fn):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            fn()
+            torch.cuda.synchronize()
+            dist.barrier()
+            with torch.cuda.graph(g, stream=side):
+                keep = [fn() for _ in range(8)]
+        torch.cuda.synchronize()
+        t = timer(lambda i: g.replay(), 10) / 8
+        tt = torch.tensor([t], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        del g, keep
+        return float(tt.item())
+
+    with torch.no_grad():
+        t_local = graph_us(lambda: blk(c))
+        t_fused = graph_us(lambda: blk(c, gather="fused"))
+    gathered = full["B"] * full["L"] * (2 * full["r"] + 1) * full["H"] * full["W"] * 4
+    return {"us_shard_lookup_only": t_local * 1e6, "us_fused_lookup_and_gather": t_fused * 1e6,
+            "bytes_gathered": gathered, "gathered_gbs_per_rank": gathered / t_fused / 1e9,
+            "what": "ONE kernel per lookup: every rank stores its shard of the result through an NVSwitch multicast "
+                    "address (multimem.st, torch symmetric memory) + a symmetric-memory barrier; bit-identical to "
+                    "lookup + NCCL all-gather (tests/test_gpu_fused_gather.py)"}
+
+
 def measure_fp16(ctx, name, reps=20):
     """The reference's "reg_cuda" mode under its default mixed precision (core/SMoEStereo.py:217-218,
     core/corr.py:31-61): fp16 feature maps -> fp16 pyramid (tcgen05 kind::f16) -> fp16 lookups, what
@@ -986,6 +1031,10 @@ def main():
                                         "what": "NCCL all-gather of ONE lookup output to every rank (optional; only a "
                                                 "non-sharded consumer needs it), timed apart from the step"}
                 del gathered
+                try:
+                    res["fused_lookup_gather"] = measure_fused_gather(ctx, name, world, rank)
+                except Exception as e:      # noqa: BLE001  (no multicast support, symmetric memory unavailable ...)
+                    res["fused_lookup_gather"] = {"unavailable": f"{type(e).__name__}: {str(e)[:200]}"}
                 strong[name] = {"n_gpus": world, "ms_per_step": t_step * 1e3, "pairs_per_s": full["B"] / t_step,
                                 "sharding": res["sharding"]}
             configs[name] = res
