@@ -58,10 +58,13 @@ with torch.no_grad():
         print("fused gather ok: bit-identical to the unsharded lookup and to lookup + NCCL all-gather", flush=True)
     # timing at BASELINE shapes
     from bench import WORKLOADS
-    for name in [a for a in sys.argv[1:] if a in WORKLOADS]:
+    for arg in [a for a in sys.argv[1:] if a.split(":")[0] in WORKLOADS]:
+        name = arg.split(":")[0]
         wl = WORKLOADS[name]
         B, H, W = wl["B"], wl["H"], wl["W"]
         mode = "batch" if B >= world and B % world == 0 else "rows"
+        if ":" in arg:
+            mode = arg.split(":")[1]                     # e.g. cfg3:rows forces the row split
         f1, f2, c = inputs(B, 256, H, W, seed=7)
         blk = sb.ShardedCorrBlock1D(f1, f2, mode=mode)
         del f1, f2
