@@ -85,6 +85,11 @@ class FusedGather:
         from .corr import _coords_plane, _on_device, _stream_ptr
         B, C, H, W = self.shape
         p = block._state.pyr
+        if torch.is_grad_enabled() and block._token is not None:
+            raise RuntimeError("gather='fused' writes through a multicast address outside autograd: use it under "
+                               "torch.no_grad() / for inference, or gather=True while training")
+        if p.dtype is not torch.float32 and not block._float_output:
+            raise RuntimeError("gather='fused' produces fp32 outputs (CorrBlock1D); use gather=True for CorrBlockFast1D")
         coords, bstride = _coords_plane(coords, p.B, p.H, p.W1)
         slot = self.pos
         self.pos = (self.pos + 1) % self.depth
