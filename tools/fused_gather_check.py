@@ -58,10 +58,13 @@ with torch.no_grad():
         print("fused gather ok: bit-identical to the unsharded lookup and to lookup + NCCL all-gather", flush=True)
     # timing at BASELINE shapes
     from bench import WORKLOADS
-    for arg in [a for a in sys.argv[1:] if a.split(":")[0] in WORKLOADS]:
+    for arg in [a for a in sys.argv[1:] if a.split(":")[0] in WORKLOADS or a[0].isdigit()]:
         name = arg.split(":")[0]
-        wl = WORKLOADS[name]
-        B, H, W = wl["B"], wl["H"], wl["W"]
+        if name[0].isdigit():                            # BxHxW[:mode] -- an ad-hoc shape
+            B, H, W = (int(v) for v in name.split("x"))
+        else:
+            wl = WORKLOADS[name]
+            B, H, W = wl["B"], wl["H"], wl["W"]
         mode = "batch" if B >= world and B % world == 0 else "rows"
         if ":" in arg:
             mode = arg.split(":")[1]                     # e.g. cfg3:rows forces the row split
