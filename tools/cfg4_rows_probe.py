@@ -13,8 +13,8 @@ from smoe_stereo_b200.corr import _lookup  # noqa: E402
 dev = torch.device("cuda", 0)
 side = torch.cuda.Stream(dev)
 PEAK = 6549.4
-W = 750
-for H in (500, 250, 125, 63, 32):
+W = int(sys.argv[1]) if len(sys.argv) > 1 else 750
+for H in ((500, 250, 125, 63, 32) if len(sys.argv) < 3 else (int(sys.argv[2]),)):
     pyr = sb.FusedPyramid(1, H, W, W, 4, torch.float32, dev)
     pyr.buffer.normal_()
     pyr.mark_missing(0b1010)
@@ -42,7 +42,7 @@ for H in (500, 250, 125, 63, 32):
     torch.cuda.synchronize()
     us = a.elapsed_time(b) * 1e3 / 20 / 32
     alg = H * W * 308
-    print(f"W=750 H={H:3d}: pyramid {pyr.buffer.numel() * 4 / 1e6:7.0f} MB  {us:6.2f} us/lookup  {us * 1e3 / (H * W):6.3f} ns/px  "
+    print(f"W={W} H={H:3d}: pyramid {pyr.buffer.numel() * 4 / 1e6:7.0f} MB  {us:6.2f} us/lookup  {us * 1e3 / (H * W):6.3f} ns/px  "
           f"{alg / us / 1e3:6.0f} GB/s algorithmic = {alg / us / 1e3 / PEAK * 100:4.1f}% of peak", flush=True)
     del gr, keep, pyr, coords
     torch.cuda.empty_cache()
