@@ -87,6 +87,8 @@ __device__ __forceinline__ void st_hint(__half* p, __half v, unsigned long long 
 // Also rejected (profiles/r02/lookup_thread_per_level_variant.log): one thread per output LEVEL for
 // L2-resident volumes (both threads of a level pair gather the segment, one interpolates the fine level,
 // the other recomputes the coarse one): the cfg1 step went from 134-138 to 157 us.
+// Occupancy is not the limiter of the streaming kernel either: capped at 48 registers (21 instead of 16
+// CTAs per SM, no spills) it measured cfg2 8.08 / cfg3 17.9 / cfg4 33.9 us against 8.31 / 17.7 / 33.4.
 template <typename VT, typename OT, int R, int NL, bool STREAM, bool SPLIT, bool LD256 = false, int HINT = 0>
 __global__ void __launch_bounds__(256)
 lookup_fwd_px_kernel(PyrDev pyr, const float* __restrict__ coords, long long coords_bstride,
