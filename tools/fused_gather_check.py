@@ -54,6 +54,15 @@ with torch.no_grad():
             torch.cuda.synchronize()
             assert torch.equal(fused, want), f"rank {rank} {mode} {B, C, H, W}: fused gather differs (iteration {it})"
         assert torch.equal(nccl, want)
+    # training blocks are refused (the multicast stores bypass autograd); every rank raises, nobody hangs
+    f1, f2, c = inputs(2, 32, 4, 64, seed=9)
+    with torch.enable_grad():
+        tr = sb.ShardedCorrBlock1D(f1.requires_grad_(True), f2, mode="batch")
+        try:
+            tr(c, gather="fused")
+            raise AssertionError("gather='fused' accepted an autograd-recording block")
+        except RuntimeError as e:
+            assert "autograd" in str(e)
     if rank == 0:
         print("fused gather ok: bit-identical to the unsharded lookup and to lookup + NCCL all-gather", flush=True)
     # timing at BASELINE shapes
